@@ -1,0 +1,35 @@
+# Top-level build: the product library, the C host, and (test infrastructure) the oracle.
+#
+#   make            -> dump1090_b200/libmodes_b200.so + dump1090-b200 (C host)
+#   make oracle     -> oracle/_build/libmodes_oracle.so (+ oracle/_ref when /root/reference exists)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Xcompiler -fPIC,-Wall,-Wextra
+CSRC      := dump1090_b200/csrc
+LIB       := dump1090_b200/libmodes_b200.so
+OBJS      := build/modes_kernels.o build/modes_api.o build/modes_resolve.o build/modes_tables.o
+
+all: $(LIB) dump1090-b200
+
+build/%.o: $(CSRC)/%.cu $(CSRC)/modes_internal.h include/modes_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
+
+build/%.o: $(CSRC)/%.cpp $(CSRC)/modes_internal.h include/modes_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -cudart static
+
+dump1090-b200: host/dump1090_b200.c include/modes_b200.h $(LIB)
+	gcc -O2 -g -Wall -W -Iinclude -o $@ host/dump1090_b200.c -Ldump1090_b200 -lmodes_b200 -Wl,-rpath,'$$ORIGIN/dump1090_b200' -lm
+
+oracle:
+	$(MAKE) -C oracle
+	if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
+
+clean:
+	rm -rf build $(LIB) dump1090-b200
+
+.PHONY: all oracle clean

@@ -1,0 +1,353 @@
+"""ctypes binding of include/modes_b200.h — the Python host side of the C ABI.
+
+Mirrors the reference's main-loop contract (dump1090.c:2968-2990): a `Decoder`
+is fed raw u8 I/Q bytes and hands back, in stream order, the messages the
+reference would pass to useModesMessage() (dump1090.c:1802).  Everything that
+computes runs in libmodes_b200.so (CUDA, sm_100a).  There is no CPU fallback:
+constructing a Decoder without a usable GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmodes_b200.so"
+
+BUFFER_BYTES = 262144
+BUFFER_SAMPLES = 131072
+CARRY_BYTES = 476
+TILE_SAMPLES = 2048
+
+EVAL_GATE_OK, EVAL_ERRORS, EVAL_DECODED, EVAL_P2_VALID = 1, 2, 4, 8
+
+
+class Config(C.Structure):
+    _fields_ = [("fix_errors", C.c_int32), ("aggressive", C.c_int32), ("check_crc", C.c_int32),
+                ("drop_eof_buffer", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32),
+                ("max_batch_bytes", C.c_uint64)]
+
+
+_MSG_A = ("errorbit aa1 aa2 aa3 phase_corrected ca iid metype mesub heading_is_valid heading "
+          "aircraft_type fflag tflag raw_latitude raw_longitude").split()
+_MSG_B = ("ew_dir ew_velocity ns_dir ns_velocity vert_rate_source vert_rate_sign vert_rate velocity "
+          "movement movement_valid ground_track ground_track_valid fs dr um identity altitude unit "
+          "nfixed pad2").split()
+
+
+class Message(C.Structure):
+    """struct modes_message == fields of struct modesMessage (dump1090.c:211-260)."""
+    _fields_ = ([("msg", C.c_uint8 * 14), ("pad0", C.c_uint8 * 2), ("msgbits", C.c_int32),
+                 ("msgtype", C.c_int32), ("crcok", C.c_int32), ("crc", C.c_uint32)]
+                + [(n, C.c_int32) for n in _MSG_A]
+                + [("flight", C.c_char * 9), ("pad1", C.c_char * 3)]
+                + [(n, C.c_int32) for n in _MSG_B]
+                + [("sample_pos", C.c_int64)])
+
+    def hex(self) -> str:
+        return bytes(self.msg[: self.msgbits // 8]).hex()
+
+    def raw_line(self) -> str:
+        """The --raw output line, dump1090.c:1324-1326."""
+        return "*" + self.hex() + ";"
+
+    def copy(self) -> "Message":
+        m = Message()
+        C.memmove(C.byref(m), C.byref(self), C.sizeof(Message))
+        return m
+
+
+class FrameEval(C.Structure):
+    _fields_ = [("msg", C.c_uint8 * 14), ("msgtype", C.c_uint8), ("flags", C.c_uint8),
+                ("errorbit", C.c_uint8), ("nfixed", C.c_uint8), ("crc", C.c_uint32)]
+
+
+class Candidate(C.Structure):
+    _fields_ = [("t", C.c_int64), ("passes", FrameEval * 2)]
+
+
+class Tile(C.Structure):
+    _fields_ = [("offset", C.c_uint32), ("count", C.c_uint32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("v", C.c_int64 * 8)]
+
+
+STAT_NAMES = ["valid_preamble", "out_of_phase", "demodulated", "goodcrc", "badcrc", "fixed",
+              "single_bit_fix", "two_bits_fix"]
+
+SINK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Message))
+
+CANDIDATE_DTYPE = np.dtype([("t", "<i8"),
+                            ("p", [("msg", "u1", 14), ("msgtype", "u1"), ("flags", "u1"), ("errorbit", "u1"),
+                                   ("nfixed", "u1"), ("crc", "<u4")], 2)], align=True)
+TILE_DTYPE = np.dtype([("offset", "<u4"), ("count", "<u4")])
+assert CANDIDATE_DTYPE.itemsize == C.sizeof(Candidate) == 56
+
+_lib = None
+
+# every symbol include/modes_b200.h declares
+EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_destroy", "modes_last_error",
+           "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
+           "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
+           "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
+           "modes_resolver_stats", "modes_decode_frame", "modes_stream", "modes_host_alloc",
+           "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
+
+
+def lib():
+    """Load libmodes_b200.so (built in-tree by `make` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make` (no CPU fallback exists)")
+        L = C.CDLL(str(LIB_PATH))
+        L.modes_create.restype = C.c_void_p
+        L.modes_create.argtypes = [C.POINTER(Config)]
+        L.modes_destroy.argtypes = [C.c_void_p]
+        L.modes_last_error.restype = C.c_char_p
+        L.modes_last_error.argtypes = [C.c_void_p]
+        L.modes_set_sink.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
+        L.modes_process.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_finish.argtypes = [C.c_void_p]
+        L.modes_reset.argtypes = [C.c_void_p]
+        L.modes_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.modes_compute_magnitude.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.modes_detect_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                          C.c_size_t, C.c_void_p]
+        L.modes_detect_wait.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.modes_detect_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.modes_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]
+        L.modes_resolver_create.restype = C.c_void_p
+        L.modes_resolver_create.argtypes = [C.POINTER(Config)]
+        L.modes_resolver_destroy.argtypes = [C.c_void_p]
+        L.modes_resolver_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, SINK_FN,
+                                         C.c_void_p]
+        L.modes_resolver_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.modes_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Message)]
+        L.modes_stream.restype = C.c_void_p
+        L.modes_stream.argtypes = [C.c_void_p]
+        L.modes_host_alloc.restype = C.c_void_p
+        L.modes_host_alloc.argtypes = [C.c_size_t]
+        L.modes_host_free.argtypes = [C.c_void_p]
+        L.modes_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
+        L.modes_launch_count.restype = C.c_uint64
+        L.modes_launch_count.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, device=0, profile=0,
+                max_batch_bytes=0) -> Config:
+    cfg = Config()
+    lib().modes_default_config(C.byref(cfg))
+    cfg.fix_errors, cfg.aggressive, cfg.check_crc = int(fix_errors), int(aggressive), int(check_crc)
+    cfg.drop_eof_buffer, cfg.device, cfg.profile = int(drop_eof_buffer), int(device), int(profile)
+    if max_batch_bytes:
+        cfg.max_batch_bytes = int(max_batch_bytes)
+    return cfg
+
+
+def tiles_for(n_buffers: int) -> int:
+    return n_buffers * (BUFFER_SAMPLES // TILE_SAMPLES) + 1
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _Collector:
+    """A sink that copies every delivered message."""
+
+    def __init__(self):
+        self.messages: list[Message] = []
+        self.fn = SINK_FN(self._on)
+
+    def _on(self, _user, mm):
+        self.messages.append(mm.contents.copy())
+
+
+class PinnedBuffer:
+    """Page-locked host memory (modes_host_alloc) exposed as a numpy u8 array."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = lib().modes_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("modes_host_alloc failed")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            lib().modes_host_free(self.ptr)
+            self.ptr = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Decoder:
+    """One GPU decode context (modes_create ... modes_destroy)."""
+
+    def __init__(self, **cfg):
+        self.cfg = make_config(**cfg)
+        self._h = lib().modes_create(C.byref(self.cfg))
+        if not self._h:
+            raise RuntimeError("modes_create failed: " + lib().modes_last_error(None).decode())
+        self._collector = _Collector()
+        lib().modes_set_sink(self._h, self._collector.fn, None)
+
+    # -- lifecycle
+    def close(self):
+        if self._h:
+            lib().modes_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(lib().modes_last_error(self._h).decode())
+
+    # -- streaming path (the --ifile main loop)
+    def process(self, data) -> None:
+        a = np.ascontiguousarray(data, dtype=np.uint8) if not isinstance(data, (bytes, bytearray)) \
+            else np.frombuffer(data, dtype=np.uint8)
+        self._check(lib().modes_process(self._h, _ptr(a), a.size))
+
+    def process_ptr(self, ptr: int, nbytes: int) -> None:
+        self._check(lib().modes_process(self._h, C.c_void_p(ptr), nbytes))
+
+    def finish(self) -> None:
+        self._check(lib().modes_finish(self._h))
+
+    def reset(self) -> None:
+        self._check(lib().modes_reset(self._h))
+        self._collector.messages = []
+
+    def take_messages(self) -> list:
+        out, self._collector.messages = self._collector.messages, []
+        return out
+
+    def decode(self, data, chunk: int | None = None) -> list:
+        """Decode a whole stream like `dump1090 --ifile`: returns the message list."""
+        self.reset()
+        a = np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else \
+            np.ascontiguousarray(data, dtype=np.uint8)
+        if chunk:
+            for off in range(0, a.size, chunk):
+                self.process(a[off: off + chunk])
+        else:
+            self.process(a)
+        self.finish()
+        return self.take_messages()
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._check(lib().modes_get_stats(self._h, C.byref(st)))
+        return dict(zip(STAT_NAMES, [int(x) for x in st.v]))
+
+    # -- stage-level entry points
+    def magnitude(self, iq: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(iq, dtype=np.uint8)
+        out = np.empty(a.size // 2, dtype=np.uint16)
+        self._check(lib().modes_compute_magnitude(self._h, _ptr(a), a.size // 2, _ptr(out)))
+        return out
+
+    def detect_device(self, d_iq_ptr: int, n_buffers: int, carry: bytes | None = None,
+                      d_candidates_ptr: int = 0, cand_capacity: int = 0, d_tiles_ptr: int = 0) -> None:
+        carr = None
+        if carry is not None:
+            assert len(carry) == CARRY_BYTES
+            carr = (C.c_uint8 * CARRY_BYTES).from_buffer_copy(carry)
+        self._check(lib().modes_detect_device(self._h, C.c_void_p(d_iq_ptr), n_buffers, carr,
+                                              C.c_void_p(d_candidates_ptr), cand_capacity,
+                                              C.c_void_p(d_tiles_ptr)))
+
+    def detect_wait(self) -> int:
+        n = C.c_uint64(0)
+        self._check(lib().modes_detect_wait(self._h, C.byref(n)))
+        return int(n.value)
+
+    def detect_fetch(self, n_buffers: int):
+        n = self.detect_wait()
+        cands = np.zeros(max(n, 1), dtype=CANDIDATE_DTYPE)
+        tiles = np.zeros(tiles_for(n_buffers), dtype=TILE_DTYPE)
+        self._check(lib().modes_detect_fetch(self._h, _ptr(cands), _ptr(tiles)))
+        return cands[:n], tiles
+
+    def resolve(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0) -> None:
+        self._check(lib().modes_resolve(self._h, _ptr(np.ascontiguousarray(cands)), _ptr(np.ascontiguousarray(tiles)),
+                                        tiles.size, buffer_base))
+
+    def decode_frame(self, frame: bytes) -> Message:
+        buf = (C.c_uint8 * 14)(*(list(frame) + [0] * (14 - len(frame))))
+        m = Message()
+        self._check(lib().modes_decode_frame(self._h, buf, C.byref(m)))
+        return m
+
+    def kernel_times_ms(self):
+        t = (C.c_float * 4)()
+        lib().modes_get_kernel_times(self._h, C.byref(t))
+        return [float(x) for x in t]
+
+    def launch_count(self) -> int:
+        return int(lib().modes_launch_count(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().modes_stream(self._h) or 0)
+
+
+class Resolver:
+    """The sequential half alone (no device): modes_resolver_*."""
+
+    def __init__(self, **cfg):
+        self.cfg = make_config(**cfg)
+        self._h = lib().modes_resolver_create(C.byref(self.cfg))
+        self._collector = _Collector()
+
+    def run(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0) -> None:
+        cands = np.ascontiguousarray(cands)
+        tiles = np.ascontiguousarray(tiles)
+        rc = lib().modes_resolver_run(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base,
+                                      self._collector.fn, None)
+        if rc:
+            raise RuntimeError("modes_resolver_run failed")
+
+    def take_messages(self):
+        out, self._collector.messages = self._collector.messages, []
+        return out
+
+    def stats(self) -> dict:
+        st = Stats()
+        lib().modes_resolver_stats(self._h, C.byref(st))
+        return dict(zip(STAT_NAMES, [int(x) for x in st.v]))
+
+    def close(self):
+        if self._h:
+            lib().modes_resolver_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

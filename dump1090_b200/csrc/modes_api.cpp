@@ -1,0 +1,496 @@
+// modes_api.cpp — the C ABI declared in include/modes_b200.h: context, device
+// workspaces, the two-slot host->device pipeline, and glue to the kernels
+// (modes_kernels.cu) and the sequential resolve (modes_resolve.cpp).
+//
+// No CPU fallback: every entry point that computes runs the CUDA kernels, and
+// modes_create() fails when no device is usable.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "modes_internal.h"
+
+using namespace modes;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t *d_iq = nullptr;         size_t iq_bytes = 0;
+    uint8_t *d_halo = nullptr;
+    uint32_t *d_cand_v = nullptr;    uint32_t cand_cap = 0;
+    modes_candidate *d_records = nullptr;
+    modes_tile *d_tiles = nullptr;   uint32_t tiles_cap = 0;
+    uint32_t *d_counters = nullptr;
+    uint8_t *h_halo = nullptr;       // pinned
+    uint32_t *h_counters = nullptr;  // pinned
+    modes_candidate *h_records = nullptr; size_t h_records_cap = 0;   // pinned
+    modes_tile *h_tiles = nullptr;   size_t h_tiles_cap = 0;          // pinned
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // in-flight batch
+    bool busy = false;
+    size_t n_buffers = 0;
+    int64_t buffer_base = 0;
+    // where this batch's results live (own workspace unless the caller supplied memory)
+    modes_candidate *out_records = nullptr;
+    modes_tile *out_tiles = nullptr;
+    uint32_t out_cap = 0;
+};
+
+}  // namespace
+
+struct modes_ctx {
+    modes_config cfg;
+    int sm_count = 148;
+    uint16_t *d_lutn = nullptr;
+    uint32_t *d_bit_syn = nullptr;
+    uint32_t *d_fix_hash = nullptr;
+    DeviceTables tab{};
+    Slot slot[2];
+    Slot detect;                      // stage-level API workspace
+    uint64_t last_detect_count = 0;
+    // stream state
+    uint8_t *pending = nullptr;       // pinned, one reference buffer
+    size_t pending_len = 0;
+    uint8_t carry[MODES_CARRY_BYTES];
+    int64_t buffers_done = 0;
+    bool finished = false;
+    ResolveState rs;
+    modes_sink_fn sink = nullptr;
+    void *sink_user = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    float times[4] = {0, 0, 0, 0};
+};
+
+namespace {
+
+int fail(modes_ctx *ctx, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_error = buf;
+    return -1;
+}
+
+#define CK(ctx, call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess)                                                          \
+            return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+uint32_t default_cand_capacity(uint64_t n_samples) {
+    uint64_t c = n_samples / 64 + 4096;
+    return c > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)c;
+}
+
+int slot_init(modes_ctx *ctx, Slot &s) {
+    CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CK(ctx, cudaMalloc(&s.d_halo, kHaloBytes));
+    CK(ctx, cudaMalloc(&s.d_counters, 4 * sizeof(uint32_t)));
+    CK(ctx, cudaMallocHost(&s.h_halo, kHaloBytes));
+    CK(ctx, cudaMallocHost(&s.h_counters, 4 * sizeof(uint32_t)));
+    for (auto &e : s.ev) CK(ctx, cudaEventCreate(&e));
+    return 0;
+}
+
+void slot_free(Slot &s) {
+    if (s.stream) cudaStreamSynchronize(s.stream);
+    cudaFree(s.d_iq); cudaFree(s.d_halo); cudaFree(s.d_cand_v); cudaFree(s.d_records);
+    cudaFree(s.d_tiles); cudaFree(s.d_counters);
+    cudaFreeHost(s.h_halo); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_records); cudaFreeHost(s.h_tiles);
+    for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot();
+}
+
+// Make sure the slot can hold a batch of n_samples (device staging only if need_iq).
+int slot_ensure(modes_ctx *ctx, Slot &s, uint64_t n_samples, bool need_iq, bool need_records) {
+    if (need_iq && s.iq_bytes < n_samples * 2) {
+        cudaFree(s.d_iq); s.d_iq = nullptr; s.iq_bytes = 0;
+        CK(ctx, cudaMalloc(&s.d_iq, n_samples * 2));
+        s.iq_bytes = n_samples * 2;
+    }
+    uint32_t cap = default_cand_capacity(n_samples);
+    if (s.cand_cap < cap) {
+        cudaFree(s.d_cand_v); s.d_cand_v = nullptr;
+        cudaFree(s.d_records); s.d_records = nullptr;
+        s.cand_cap = 0;
+        CK(ctx, cudaMalloc(&s.d_cand_v, (size_t)cap * sizeof(uint32_t)));
+        s.cand_cap = cap;
+    }
+    if (need_records && !s.d_records) CK(ctx, cudaMalloc(&s.d_records, (size_t)s.cand_cap * sizeof(modes_candidate)));
+    uint32_t nt = tiles_for(n_samples);
+    if (s.tiles_cap < nt) {
+        cudaFree(s.d_tiles); s.d_tiles = nullptr;
+        CK(ctx, cudaMalloc(&s.d_tiles, (size_t)nt * sizeof(modes_tile)));
+        s.tiles_cap = nt;
+    }
+    return 0;
+}
+
+int host_ensure(modes_ctx *ctx, Slot &s, size_t n_records, size_t n_tiles) {
+    if (s.h_records_cap < n_records) {
+        cudaFreeHost(s.h_records); s.h_records = nullptr; s.h_records_cap = 0;
+        size_t cap = n_records + n_records / 2 + 1024;
+        CK(ctx, cudaMallocHost(&s.h_records, cap * sizeof(modes_candidate)));
+        s.h_records_cap = cap;
+    }
+    if (s.h_tiles_cap < n_tiles) {
+        cudaFreeHost(s.h_tiles); s.h_tiles = nullptr; s.h_tiles_cap = 0;
+        CK(ctx, cudaMallocHost(&s.h_tiles, n_tiles * sizeof(modes_tile)));
+        s.h_tiles_cap = n_tiles;
+    }
+    return 0;
+}
+
+// Queue one batch on the slot's stream: (optional H2D) + halo + scan + frame evaluation.
+int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, size_t n_buffers,
+           const uint8_t *carry476, modes_candidate *d_records_ext, uint32_t cap_ext, modes_tile *d_tiles_ext) {
+    const uint64_t n_samples = (uint64_t)n_buffers * kBufSamples;
+    if (n_samples + kHaloSamples >= (1ull << 32)) return fail(ctx, "batch too large: %zu buffers", n_buffers);
+    if (slot_ensure(ctx, s, n_samples, host_iq != nullptr, d_records_ext == nullptr)) return -1;
+    if (host_iq) {
+        CK(ctx, cudaMemcpyAsync(s.d_iq, host_iq, n_samples * 2, cudaMemcpyHostToDevice, s.stream));
+        d_iq = s.d_iq;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0) return fail(ctx, "device I/Q pointer must be 16-byte aligned");
+    memset(s.h_halo, 127, kHaloBytes);                                    // dump1090.c:344 no-signal
+    if (carry476) memcpy(s.h_halo + (kHaloBytes - MODES_CARRY_BYTES), carry476, MODES_CARRY_BYTES);
+    CK(ctx, cudaMemcpyAsync(s.d_halo, s.h_halo, kHaloBytes, cudaMemcpyHostToDevice, s.stream));
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(uint32_t), s.stream));
+
+    BatchView in{static_cast<const uint8_t *>(d_iq), s.d_halo, n_samples};
+    s.out_records = d_records_ext ? d_records_ext : s.d_records;
+    s.out_tiles = d_tiles_ext ? d_tiles_ext : s.d_tiles;
+    s.out_cap = d_records_ext ? (cap_ext < s.cand_cap ? cap_ext : s.cand_cap) : s.cand_cap;
+    ScanOutputs so{s.d_cand_v, s.out_cap, s.out_tiles, s.d_counters};
+
+    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[0], s.stream));
+    launch_scan(in, ctx->tab, so, ctx->sm_count, s.stream);
+    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[1], s.stream));
+    launch_eval(in, ctx->tab, so, s.out_records, ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->sm_count, s.stream);
+    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[2], s.stream));
+    CK(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    CK(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaEventRecord(s.ev[3], s.stream));
+    s.busy = true;
+    s.n_buffers = n_buffers;
+    return 0;
+}
+
+// Wait for the slot's batch; returns the number of candidates stored.
+int wait_batch(modes_ctx *ctx, Slot &s, uint64_t *n_out) {
+    CK(ctx, cudaEventSynchronize(s.ev[3]));
+    if (ctx->cfg.profile) {
+        cudaEventElapsedTime(&ctx->times[0], s.ev[0], s.ev[1]);
+        cudaEventElapsedTime(&ctx->times[1], s.ev[1], s.ev[2]);
+        cudaEventElapsedTime(&ctx->times[2], s.ev[0], s.ev[2]);
+        ctx->times[3] = 2.0f;
+    }
+    if (s.h_counters[1] || s.h_counters[0] > s.out_cap)
+        return fail(ctx, "candidate capacity exceeded: %u found, room for %u", s.h_counters[0], s.out_cap);
+    *n_out = s.h_counters[0];
+    return 0;
+}
+
+// Fetch the slot's results to pinned host memory and run the sequential resolve.
+int collect(modes_ctx *ctx, Slot &s) {
+    if (!s.busy) return 0;
+    s.busy = false;
+    uint64_t n = 0;
+    if (wait_batch(ctx, s, &n)) return -1;
+    const size_t nt = tiles_for((uint64_t)s.n_buffers * kBufSamples);
+    if (host_ensure(ctx, s, n, nt)) return -1;
+    if (n) CK(ctx, cudaMemcpyAsync(s.h_records, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaMemcpyAsync(s.h_tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaStreamSynchronize(s.stream));
+    ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
+    resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->sink, ctx->sink_user);
+    return 0;
+}
+
+// Decode n_buffers whole reference buffers that sit in host memory.
+int run_buffers(modes_ctx *ctx, const uint8_t *host_iq, size_t n_buffers) {
+    size_t max_b = (size_t)(ctx->cfg.max_batch_bytes / MODES_BUFFER_BYTES);
+    if (max_b < 1) max_b = 1;
+    int cur = 0;
+    while (n_buffers) {
+        size_t nb = n_buffers < max_b ? n_buffers : max_b;
+        Slot &s = ctx->slot[cur];
+        if (collect(ctx, s)) return -1;                                  // slot may still hold batch b-2
+        s.buffer_base = ctx->buffers_done;
+        if (submit(ctx, s, host_iq, nullptr, nb, ctx->carry, nullptr, 0, nullptr)) return -1;
+        memcpy(ctx->carry, host_iq + nb * MODES_BUFFER_BYTES - MODES_CARRY_BYTES, MODES_CARRY_BYTES);
+        ctx->buffers_done += (int64_t)nb;
+        host_iq += nb * MODES_BUFFER_BYTES;
+        n_buffers -= nb;
+        cur ^= 1;
+        if (collect(ctx, ctx->slot[cur])) return -1;                     // resolve batch b-1 while b runs
+    }
+    if (collect(ctx, ctx->slot[cur])) return -1;
+    if (collect(ctx, ctx->slot[cur ^ 1])) return -1;
+    return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------- C ABI
+
+extern "C" {
+
+int modes_abi_version(void) { return MODES_B200_ABI_VERSION; }
+
+void modes_default_config(modes_config *cfg) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->fix_errors = 1;
+    cfg->aggressive = 0;
+    cfg->check_crc = 1;
+    cfg->drop_eof_buffer = 0;
+    cfg->device = 0;
+    cfg->profile = 0;
+    cfg->max_batch_bytes = 256ull << 20;
+}
+
+const char *modes_last_error(const modes_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void modes_destroy(modes_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
+    cudaFree(ctx->d_lutn); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
+    cudaFreeHost(ctx->pending);
+    delete ctx;
+}
+
+static int create_impl(modes_ctx *ctx) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (ctx->cfg.device < 0 || ctx->cfg.device >= ndev) return fail(nullptr, "device %d out of range", ctx->cfg.device);
+    CK(nullptr, cudaSetDevice(ctx->cfg.device));
+    cudaDeviceProp prop;
+    CK(nullptr, cudaGetDeviceProperties(&prop, ctx->cfg.device));
+    if (prop.major < 10) return fail(nullptr, "device %d is sm_%d%d; kernels are built for sm_100a only", ctx->cfg.device, prop.major, prop.minor);
+    ctx->sm_count = prop.multiProcessorCount;
+
+    std::vector<uint16_t> lutn(kNLutEntries);
+    uint32_t syn[112], hash[kFixHashSlots];
+    build_lutn(lutn.data());
+    build_bit_syndromes(syn);
+    if (!build_fix_hash(syn, hash)) return fail(nullptr, "internal: syndrome hash construction failed");
+    CK(nullptr, cudaMalloc(&ctx->d_lutn, kNLutEntries * sizeof(uint16_t)));
+    CK(nullptr, cudaMalloc(&ctx->d_bit_syn, sizeof(syn)));
+    CK(nullptr, cudaMalloc(&ctx->d_fix_hash, sizeof(hash)));
+    CK(nullptr, cudaMemcpy(ctx->d_lutn, lutn.data(), kNLutEntries * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(ctx->d_bit_syn, syn, sizeof(syn), cudaMemcpyHostToDevice));
+    CK(nullptr, cudaMemcpy(ctx->d_fix_hash, hash, sizeof(hash), cudaMemcpyHostToDevice));
+    ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_bit_syn, ctx->d_fix_hash};
+    CK(nullptr, cudaMallocHost(&ctx->pending, MODES_BUFFER_BYTES));
+    for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->detect})
+        if (slot_init(ctx, *s)) { g_create_error = ctx->err; return -1; }
+    return 0;
+}
+
+modes_ctx *modes_create(const modes_config *cfg) {
+    modes_ctx *ctx = new (std::nothrow) modes_ctx();
+    if (!ctx) { g_create_error = "out of memory"; return nullptr; }
+    if (cfg) ctx->cfg = *cfg; else modes_default_config(&ctx->cfg);
+    if (ctx->cfg.max_batch_bytes == 0) ctx->cfg.max_batch_bytes = 256ull << 20;
+    ctx->rs.reset();
+    memset(ctx->carry, 127, sizeof(ctx->carry));
+    if (create_impl(ctx)) { modes_destroy(ctx); return nullptr; }
+    return ctx;
+}
+
+int modes_set_sink(modes_ctx *ctx, modes_sink_fn fn, void *user) {
+    if (!ctx) return -1;
+    ctx->sink = fn; ctx->sink_user = user;
+    return 0;
+}
+
+int modes_reset(modes_ctx *ctx) {
+    if (!ctx) return -1;
+    ctx->rs.reset();
+    ctx->pending_len = 0;
+    ctx->buffers_done = 0;
+    ctx->finished = false;
+    memset(ctx->carry, 127, sizeof(ctx->carry));
+    return 0;
+}
+
+int modes_process(modes_ctx *ctx, const uint8_t *iq, size_t nbytes) {
+    if (!ctx) return -1;
+    if (ctx->finished) return fail(ctx, "modes_process after modes_finish; call modes_reset first");
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    if (ctx->pending_len) {
+        size_t take = MODES_BUFFER_BYTES - ctx->pending_len;
+        if (take > nbytes) take = nbytes;
+        memcpy(ctx->pending + ctx->pending_len, iq, take);
+        ctx->pending_len += take; iq += take; nbytes -= take;
+        if (ctx->pending_len < MODES_BUFFER_BYTES) return 0;
+        if (run_buffers(ctx, ctx->pending, 1)) return -1;
+        ctx->pending_len = 0;
+    }
+    size_t whole = nbytes / MODES_BUFFER_BYTES;
+    if (whole && run_buffers(ctx, iq, whole)) return -1;
+    iq += whole * MODES_BUFFER_BYTES; nbytes -= whole * MODES_BUFFER_BYTES;
+    if (nbytes) { memcpy(ctx->pending, iq, nbytes); ctx->pending_len = nbytes; }
+    return 0;
+}
+
+int modes_finish(modes_ctx *ctx) {
+    if (!ctx) return -1;
+    if (ctx->finished) return 0;
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    ctx->finished = true;
+    // The read that hits EOF still hands a 127-padded buffer to the decoder (dump1090.c:496-510);
+    // whether it is decoded is the reference's race, made a switch here.
+    memset(ctx->pending + ctx->pending_len, 127, MODES_BUFFER_BYTES - ctx->pending_len);
+    ctx->pending_len = 0;
+    if (ctx->cfg.drop_eof_buffer) return 0;
+    return run_buffers(ctx, ctx->pending, 1);
+}
+
+int modes_get_stats(const modes_ctx *ctx, modes_stats *out) {
+    if (!ctx || !out) return -1;
+    memcpy(out->v, ctx->rs.stats, sizeof(out->v));
+    return 0;
+}
+
+int modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples, uint16_t *mag) {
+    if (!ctx) return -1;
+    if (!nsamples) return 0;
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    uint8_t *d_iq = nullptr; uint16_t *d_mag = nullptr;
+    cudaStream_t st = ctx->detect.stream;
+    CK(ctx, cudaMalloc(&d_iq, nsamples * 2));
+    if (cudaMalloc(&d_mag, nsamples * 2) != cudaSuccess) { cudaFree(d_iq); return fail(ctx, "cudaMalloc failed"); }
+    cudaMemcpyAsync(d_iq, iq, nsamples * 2, cudaMemcpyHostToDevice, st);
+    launch_magnitude(d_iq, d_mag, nsamples, ctx->d_lutn, st);
+    ctx->launches++;
+    cudaMemcpyAsync(mag, d_mag, nsamples * 2, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_iq); cudaFree(d_mag);
+    if (e != cudaSuccess) return fail(ctx, "magnitude kernel failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, const uint8_t *carry476,
+                        void *d_candidates, size_t cand_capacity, void *d_tiles) {
+    if (!ctx) return -1;
+    if (!d_iq || !n_buffers) return fail(ctx, "modes_detect_device: empty input");
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    uint32_t cap = cand_capacity > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cand_capacity;
+    return submit(ctx, ctx->detect, nullptr, d_iq, n_buffers, carry476,
+                  static_cast<modes_candidate *>(d_candidates), cap, static_cast<modes_tile *>(d_tiles));
+}
+
+int modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates) {
+    if (!ctx) return -1;
+    if (!ctx->detect.busy) return fail(ctx, "modes_detect_wait without modes_detect_device");
+    uint64_t n = 0;
+    if (wait_batch(ctx, ctx->detect, &n)) return -1;
+    ctx->last_detect_count = n;
+    if (n_candidates) *n_candidates = n;
+    return 0;
+}
+
+int modes_detect_fetch(modes_ctx *ctx, modes_candidate *candidates, modes_tile *tiles) {
+    if (!ctx) return -1;
+    Slot &s = ctx->detect;
+    if (!s.busy) return fail(ctx, "modes_detect_fetch without modes_detect_device");
+    uint64_t n = 0;
+    if (wait_batch(ctx, s, &n)) return -1;
+    const size_t nt = tiles_for((uint64_t)s.n_buffers * kBufSamples);
+    if (n && candidates)
+        CK(ctx, cudaMemcpyAsync(candidates, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
+    if (tiles) CK(ctx, cudaMemcpyAsync(tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
+    CK(ctx, cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+int modes_resolve(modes_ctx *ctx, const modes_candidate *candidates, const modes_tile *tiles, size_t n_tiles,
+                  int64_t buffer_base) {
+    if (!ctx || !tiles) return -1;
+    ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
+    resolve_candidates(ctx->rs, rc, candidates, tiles, n_tiles, buffer_base, ctx->sink, ctx->sink_user);
+    return 0;
+}
+
+struct modes_resolver { ResolveState rs; ResolveConfig rc; };
+
+modes_resolver *modes_resolver_create(const modes_config *cfg) {
+    modes_resolver *r = new (std::nothrow) modes_resolver();
+    if (!r) return nullptr;
+    modes_config c;
+    if (cfg) c = *cfg; else modes_default_config(&c);
+    r->rc = ResolveConfig{c.fix_errors, c.aggressive, c.check_crc};
+    r->rs.reset();
+    return r;
+}
+
+void modes_resolver_destroy(modes_resolver *r) { delete r; }
+
+int modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                       size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user) {
+    if (!r || !tiles) return -1;
+    resolve_candidates(r->rs, r->rc, candidates, tiles, n_tiles, buffer_base, sink, user);
+    return 0;
+}
+
+int modes_resolver_stats(const modes_resolver *r, modes_stats *out) {
+    if (!r || !out) return -1;
+    memcpy(out->v, r->rs.stats, sizeof(out->v));
+    return 0;
+}
+
+int modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out) {
+    if (!ctx || !msg || !out) return -1;
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    uint8_t *d_in = nullptr; modes_frame_eval *d_out = nullptr; modes_frame_eval h;
+    cudaStream_t st = ctx->detect.stream;
+    CK(ctx, cudaMalloc(&d_in, 16));
+    if (cudaMalloc(&d_out, sizeof(h)) != cudaSuccess) { cudaFree(d_in); return fail(ctx, "cudaMalloc failed"); }
+    cudaMemcpyAsync(d_in, msg, 14, cudaMemcpyHostToDevice, st);
+    launch_eval_frames(d_in, d_out, 1, ctx->tab, ctx->cfg.fix_errors, ctx->cfg.aggressive, st);
+    ctx->launches++;
+    cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(ctx, "frame kernel failed: %s", cudaGetErrorString(e));
+    finish_message(ctx->rs, h, out);
+    out->sample_pos = -1;
+    return 0;
+}
+
+void *modes_stream(modes_ctx *ctx) { return ctx ? (void *)ctx->detect.stream : nullptr; }
+
+void *modes_host_alloc(size_t nbytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void modes_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+int modes_get_kernel_times(const modes_ctx *ctx, float ms[4]) {
+    if (!ctx || !ms) return -1;
+    memcpy(ms, ctx->times, sizeof(ctx->times));
+    return 0;
+}
+
+uint64_t modes_launch_count(const modes_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+// modes_internal.h — declarations shared by the CUDA kernels (modes_kernels.cu),
+// the host resolve (modes_resolve.cpp) and the C-ABI glue (modes_api.cpp).
+// Product code; never includes anything from oracle/.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "modes_b200.h"
+
+namespace modes {
+
+// ---- geometry of the "virtual" sample array a batch is scanned over --------
+// A batch is n_buffers whole reference buffers (131072 new samples each,
+// dump1090.c:54) resident in HBM, preceded by the 238 samples the reference
+// carries over from the previous buffer (dump1090.c:481).  The carry lives in
+// a separate 480-byte device block (2 unused samples + 238 carry) so that the
+// body keeps its 16-byte alignment:
+//     virtual index v in [0, 240)      -> halo[v]
+//     virtual index v in [240, 240+N)  -> body[v-240]
+// The reference's buffer-relative position of v is t = v - 2 = 131072*k + j,
+// and the scan visits j in [0, 131070) (dump1090.c:1593).
+constexpr int      kHaloSamples  = 240;
+constexpr int      kHaloBytes    = 480;
+constexpr int      kTileSamples  = MODES_TILE_SAMPLES;          // one scan tile
+constexpr uint32_t kBufSamples   = MODES_BUFFER_SAMPLES;
+constexpr uint32_t kScanLimit    = kBufSamples - 2;             // j < 131070
+constexpr int      kNLutEntries  = 32769;                       // magnitude by i*i+q*q
+constexpr int      kFixHashSlots = 256;
+
+struct DeviceTables {
+    const uint16_t *lutn;        // [32769] round(sqrt(n)*360), dump1090.c:362 keyed by n=i*i+q*q
+    const uint32_t *bit_syn;     // [112] syndrome of a single flipped bit (dump1090.c:683-698 + parity bits)
+    const uint32_t *fix_hash;    // [256] open-addressed inverse of bit_syn: (syndrome<<8 | pos), 0xFFFFFFFF empty
+};
+
+struct BatchView {
+    const uint8_t *body;         // n_samples*2 bytes, 16-byte aligned
+    const uint8_t *halo;         // kHaloBytes, 16-byte aligned
+    uint64_t       n_samples;    // N = n_buffers * 131072
+};
+
+struct ScanOutputs {
+    uint32_t   *cand_v;          // virtual positions of candidates, tile by tile
+    uint32_t    cand_capacity;
+    modes_tile *tiles;           // [n_tiles]
+    uint32_t   *counters;        // [0] candidates found (may exceed capacity), [1] overflow flag
+};
+
+inline uint32_t tiles_for(uint64_t n_samples) {
+    return (uint32_t)((n_samples + kHaloSamples + kTileSamples - 1) / kTileSamples);
+}
+
+// Kernel launchers (modes_kernels.cu).  All asynchronous on `stream`.
+void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
+                 cudaStream_t stream);
+void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
+                 modes_candidate *records, int fix_errors, int aggressive, int sm_count,
+                 cudaStream_t stream);
+void launch_magnitude(const uint8_t *d_iq, uint16_t *d_mag, uint64_t n_samples, const uint16_t *lutn,
+                      cudaStream_t stream);
+// CRC / fix on raw frame bytes (hex door): n frames of 14 bytes -> n modes_frame_eval.
+void launch_eval_frames(const uint8_t *d_frames, modes_frame_eval *d_out, uint32_t n, const DeviceTables &tab,
+                        int fix_errors, int aggressive, cudaStream_t stream);
+
+// Host-side table construction (modes_tables.cpp).
+void build_lutn(uint16_t *out /*[32769]*/);
+void build_bit_syndromes(uint32_t *out /*[112]*/);
+bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out /*[256]*/);
+
+// ---- sequential resolve (modes_resolve.cpp) --------------------------------
+struct ResolveState {
+    uint32_t icao[1024];         // dump1090.c:335: address per slot (TTL: never expires within a run)
+    int64_t  stats[8];
+    int64_t  cur_buffer;         // buffer whose skip state is live, -1 = none
+    uint32_t next_j;             // first position not skipped in cur_buffer
+    void reset();
+};
+
+struct ResolveConfig { int fix_errors, aggressive, check_crc; };
+
+void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base,
+                        modes_sink_fn sink, void *user);
+// The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
+int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
+
+}  // namespace modes

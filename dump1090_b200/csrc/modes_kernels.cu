@@ -1,0 +1,577 @@
+// modes_kernels.cu — sm_100a kernels of the Mode S demodulator.
+//
+//   scan_kernel   (K1)  u8 I/Q -> squared magnitude -> preamble tests, fused.
+//                       Replaces computeMagnitudeVector (dump1090.c:1454-1469) and
+//                       the per-position preamble tests of detectModeS
+//                       (dump1090.c:1602-1650).  HBM-bound: 2 bytes read per sample,
+//                       nothing written but the (sparse) candidate list.
+//   eval_kernel   (K2)  one warp per candidate: bit slicing (dump1090.c:1668-1706),
+//                       delta gate (:1713-1726), phase-corrected retry (:1498-1558),
+//                       CRC syndrome (:703-742) and syndrome-table repair
+//                       (:795-894), both passes, as pure functions of the samples.
+//   magnitude_kernel    computeMagnitudeVector alone, materialising u16 (tests only).
+//   eval_frames_kernel  CRC + repair on raw frame bytes (hex door, :2472-2502).
+//
+// Integer-only; no tensor cores (there is no dense contraction on this path).
+//
+// Exactness notes.
+//  * The reference compares magnitudes m = round(360*sqrt(n)), n = i*i+q*q with
+//    i,q in [0,128].  m is strictly increasing over the reachable values of n
+//    (consecutive integers n <= 32400 differ by >= 1.0 in 360*sqrt(n); the only
+//    reachable values above are 32513 and 32768), so every magnitude-vs-magnitude
+//    comparison of dump1090.c:1602-1611 is decided exactly on n.  Only the
+//    "high" tests (:1624-1642) and the frame evaluation need m itself, read from
+//    a table keyed by n that the host builds with the reference's formula.
+//  * "copy the previous bit" slicing (dump1090.c:1675) and the decision chain
+//    inside applyPhaseCorrection are both "last definite value wins" scans; on
+//    ballot words they are the carry chain of one 128-bit addition (fill128).
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "modes_internal.h"
+
+namespace modes {
+
+// ------------------------------------------------------------------ helpers
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+// 16-byte chunk c of the virtual sample array (8 samples).  Chunks past the end
+// read as "no signal" (127,127).
+__device__ __forceinline__ uint4 load_vchunk(const BatchView &in, uint64_t c, uint64_t n_vchunks) {
+    if (c >= n_vchunks) return make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+    const uint4 *p = (c < kHaloSamples / 8) ? reinterpret_cast<const uint4 *>(in.halo) + c
+                                            : reinterpret_cast<const uint4 *>(in.body) + (c - kHaloSamples / 8);
+    return ldg_stream(p);
+}
+
+// Two I/Q pairs (bytes I0 Q0 I1 Q1) -> two squared magnitudes packed as u16x2.
+// |b-127| per byte in one SIMD instruction, then a byte dot product each.
+__device__ __forceinline__ uint32_t iq2_to_n2(uint32_t w) {
+    uint32_t a = __vabsdiffu4(w, 0x7f7f7f7fu);
+    uint32_t n0 = __dp4a(a & 0x0000ffffu, a, 0u);
+    uint32_t n1 = __dp4a(a & 0xffff0000u, a, 0u);
+    return n0 | (n1 << 16);
+}
+
+__device__ __forceinline__ uint4 iq8_to_n8(uint4 raw) {
+    return make_uint4(iq2_to_n2(raw.x), iq2_to_n2(raw.y), iq2_to_n2(raw.z), iq2_to_n2(raw.w));
+}
+
+// One sample of the virtual array -> squared magnitude.
+__device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
+    const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);
+    uint32_t w = *reinterpret_cast<const uint16_t *>(p);
+    uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
+    return __dp4a(a, a, 0u);
+}
+
+// ------------------------------------------------------------------ K1: scan
+
+constexpr int kScanThreads = 256;      // 8 samples per thread = one 2048-sample tile per pass
+
+// Exact version of the tests of dump1090.c:1624-1642 for a position that already
+// passed the ten comparisons; ns = squared magnitudes of the tile (+16 lookahead).
+__device__ __forceinline__ bool high_tests(const uint16_t *ns, int pos, const uint16_t *__restrict__ lutn) {
+    int m0 = __ldg(lutn + ns[pos]),      m2 = __ldg(lutn + ns[pos + 2]);
+    int m7 = __ldg(lutn + ns[pos + 7]),  m9 = __ldg(lutn + ns[pos + 9]);
+    int m4 = __ldg(lutn + ns[pos + 4]),  m5 = __ldg(lutn + ns[pos + 5]);
+    int m11 = __ldg(lutn + ns[pos + 11]), m12 = __ldg(lutn + ns[pos + 12]);
+    int m13 = __ldg(lutn + ns[pos + 13]), m14 = __ldg(lutn + ns[pos + 14]);
+    int high = (m0 + m2 + m7 + m9) / 6;
+    return m4 < high && m5 < high && m11 < high && m12 < high && m13 < high && m14 < high;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
+    __shared__ uint4 s_n[2][kScanThreads + 2];      // u16 squared magnitudes, +16 lookahead
+    __shared__ uint32_t s_mask[2][kScanThreads / 4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t n_vsamples = in.n_samples + kHaloSamples;
+    const uint64_t n_vchunks = n_vsamples / 8;
+    const uint64_t t_end = in.n_samples;            // valid t < N
+
+    uint32_t tile = blockIdx.x;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (tile < n_tiles) raw = load_vchunk(in, (uint64_t)tile * kScanThreads + tid, n_vchunks);
+
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const uint64_t chunk0 = (uint64_t)tile * kScanThreads;
+        // prefetch the next tile's chunk while this one is processed
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        if (tile + gridDim.x < n_tiles)
+            nxt = load_vchunk(in, (uint64_t)(tile + gridDim.x) * kScanThreads + tid, n_vchunks);
+
+        s_n[buf][tid] = iq8_to_n8(raw);
+        if (tid < 2) s_n[buf][kScanThreads + tid] = iq8_to_n8(load_vchunk(in, chunk0 + kScanThreads + tid, n_vchunks));
+        __syncthreads();
+
+        // window of 24 squared magnitudes starting at this thread's first sample
+        uint4 a = s_n[buf][tid], b = s_n[buf][tid + 1], c = s_n[buf][tid + 2];
+        uint32_t x[24];
+        const uint32_t pk[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int k = 0; k < 12; k++) { x[2 * k] = pk[k] & 0xffffu; x[2 * k + 1] = pk[k] >> 16; }
+
+        // ten comparisons of dump1090.c:1602-1611, exact on squared magnitudes
+        uint32_t mask = 0;
+#pragma unroll
+        for (int p = 0; p < 8; p++) {
+            bool ok = x[p] > x[p + 1] && x[p + 1] < x[p + 2] && x[p + 2] > x[p + 3] && x[p + 3] < x[p] &&
+                      x[p + 4] < x[p] && x[p + 5] < x[p] && x[p + 6] < x[p] && x[p + 7] > x[p + 8] &&
+                      x[p + 8] < x[p + 9] && x[p + 9] > x[p + 6];
+            mask |= ok ? (1u << p) : 0u;
+        }
+        // positions the reference never tests: t < 0, j >= 131070 (dump1090.c:1593), past the batch
+        if (mask) {
+            const uint64_t v0 = (chunk0 + tid) * 8;
+#pragma unroll
+            for (int p = 0; p < 8; p++) {
+                uint64_t v = v0 + p;
+                bool valid = v >= 2 && (v - 2) < t_end && (((uint32_t)(v - 2)) & (kBufSamples - 1)) < kScanLimit;
+                if (!valid) mask &= ~(1u << p);
+            }
+        }
+        reinterpret_cast<uint8_t *>(s_mask[buf])[tid] = (uint8_t)mask;
+        __syncthreads();
+
+        // One warp (rotating) finishes the tile: exact "high" tests on the few
+        // survivors, ordered compaction, one atomic per tile.
+        if (warp == (it & 7)) {
+            const uint16_t *ns = reinterpret_cast<const uint16_t *>(s_n[buf]);
+            uint32_t keep[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t w = s_mask[buf][2 * lane + h], k = 0;
+                for (uint32_t r = w; r; r &= r - 1) {
+                    int bit = __ffs(r) - 1;
+                    if (high_tests(ns, 64 * lane + 32 * h + bit, lutn)) k |= 1u << bit;
+                }
+                keep[h] = k;
+            }
+            uint32_t cnt = __popc(keep[0]) + __popc(keep[1]);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (lane == 0 && total) base = atomicAdd(&out.counters[0], total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t idx = base + incl - cnt;
+            const uint32_t vbase = (uint32_t)(chunk0 * 8) + 64 * lane;
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                for (uint32_t r = keep[h]; r; r &= r - 1) {
+                    if (idx < out.cand_capacity) out.cand_v[idx] = vbase + 32 * h + (__ffs(r) - 1);
+                    idx++;
+                }
+            if (lane == 0) {
+                uint32_t stored = total;
+                if (base + total > out.cand_capacity) {
+                    stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
+                    out.counters[1] = 1;
+                }
+                modes_tile tl; tl.offset = base; tl.count = stored;
+                out.tiles[tile] = tl;
+            }
+        }
+        raw = nxt;
+    }
+}
+
+void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
+                 cudaStream_t stream) {
+    uint32_t n_tiles = tiles_for(in.n_samples);
+    uint32_t grid = (uint32_t)sm_count * 6;
+    if (grid > n_tiles) grid = n_tiles;
+    scan_kernel<<<grid, kScanThreads, 0, stream>>>(in, tab.lutn, out, n_tiles);
+}
+
+// ------------------------------------------------------- K2: frame evaluation
+
+struct U128 { uint64_t lo, hi; };
+
+// Bits with D=1 are "definite" and take their value from O; bits with D=0 copy
+// the nearest definite bit below.  That is the carry-out of (O|~D) + O.
+__device__ __forceinline__ U128 fill128(U128 D, U128 O) {
+    uint64_t a0 = O.lo | ~D.lo, a1 = O.hi | ~D.hi;
+    uint64_t s0 = a0 + O.lo;
+    uint64_t c = s0 < a0 ? 1ull : 0ull;
+    uint64_t s1 = a1 + O.hi + c;
+    uint64_t ci0 = s0 ^ a0 ^ O.lo, ci1 = s1 ^ a1 ^ O.hi;     // carry INTO each bit
+    U128 f;
+    f.lo = (ci0 >> 1) | (ci1 << 63);
+    f.hi = ci1 >> 1;                                          // top bit unused (bits >= 112 are padding)
+    return f;
+}
+
+__device__ __forceinline__ U128 ballot128(bool p0, bool p1, bool p2, bool p3) {
+    uint32_t w0 = __ballot_sync(0xffffffffu, p0), w1 = __ballot_sync(0xffffffffu, p1);
+    uint32_t w2 = __ballot_sync(0xffffffffu, p2), w3 = __ballot_sync(0xffffffffu, p3);
+    U128 r; r.lo = w0 | ((uint64_t)w1 << 32); r.hi = w2 | ((uint64_t)w3 << 32);
+    return r;
+}
+
+__device__ __forceinline__ uint32_t bit_of(U128 x, int b) {
+    return (uint32_t)(((b < 64) ? (x.lo >> b) : (x.hi >> (b - 64))) & 1ull);
+}
+
+// Reverse the 112 valid bits (bit b <-> bit 111-b).
+__device__ __forceinline__ U128 rev112(U128 x) {
+    uint64_t rl = __brevll(x.hi), rh = __brevll(x.lo);       // 128-bit reversal: bit b -> 127-b
+    U128 r; r.lo = (rl >> 16) | (rh << 48); r.hi = rh >> 16;  // then down by 16
+    return r;
+}
+
+__device__ __forceinline__ int scale_sample(int v, int s) {   // dump1090.c:1473-1476
+    uint32_t r = ((uint32_t)v * (uint32_t)s) >> 14;
+    return r > 65535u ? 65535 : (int)r;
+}
+
+struct PassResult {
+    uint32_t W[4];          // frame bytes as big-endian words (W[3]: top 16 bits)
+    uint32_t msgtype, flags, errorbit, nfixed, crc;
+};
+
+__device__ __forceinline__ uint32_t fix_hash_of(uint32_t s) { return (s * 0x9E3779B1u) >> 24; }
+
+// Position whose single-bit syndrome is s, or -1.
+__device__ __forceinline__ int syndrome_pos(const uint32_t *s_hash, uint32_t s) {
+    uint32_t h = fix_hash_of(s);
+    for (int i = 0; i < kFixHashSlots; i++) {
+        uint32_t e = s_hash[(h + i) & (kFixHashSlots - 1)];
+        if (e == 0xFFFFFFFFu) return -1;
+        if ((e >> 8) == s) return (int)(e & 0xff);
+    }
+    return -1;
+}
+
+// CRC syndrome + repair on frame bits F (bit b of the frame at bit b of F).
+// dump1090.c:1099-1128 with :733-742 and :854-894.  Warp-uniform result.
+__device__ __forceinline__ void crc_and_fix(U128 &F, int msgbits, uint32_t msgtype, int fix_errors, int aggressive,
+                                            const uint32_t *s_syn, const uint32_t *s_hash, int lane,
+                                            uint32_t &crc, uint32_t &errorbit, uint32_t &nfixed) {
+    const int off = 112 - msgbits;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int b = 32 * r + lane;
+        if (b < msgbits && bit_of(F, b)) acc ^= s_syn[b + off];
+    }
+    uint32_t S = __reduce_xor_sync(0xffffffffu, acc);
+    errorbit = 0xFF; nfixed = 0;
+    if (S != 0 && fix_errors && (msgtype == 11 || msgtype == 17 || msgtype == 18)) {
+        const int pmin = off > 5 ? off : 5;                  // table covers frame positions 5..111
+        // single-bit patterns
+        int hit = -1;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int p = 32 * r + lane;
+            uint32_t m = __ballot_sync(0xffffffffu, p >= pmin && p < 112 && s_syn[p] == S);
+            if (m && hit < 0) hit = 32 * r + (__ffs(m) - 1);
+        }
+        if (hit >= 0) {
+            int fb = hit - off;
+            if (fb < 64) F.lo ^= 1ull << fb; else F.hi ^= 1ull << (fb - 64);
+            errorbit = fb; nfixed = 1; S = 0;
+        } else if (aggressive) {
+            // two-bit patterns p<q: S ^ syn[p] must be the syndrome of some q
+            int hp = -1, hq = -1;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                int p = 32 * r + lane, q = -1;
+                if (p >= pmin && p < 112) {
+                    q = syndrome_pos(s_hash, S ^ s_syn[p]);
+                    if (q <= p || q < pmin) q = -1;
+                }
+                uint32_t m = __ballot_sync(0xffffffffu, q >= 0);
+                if (m && hp < 0) {
+                    int src = __ffs(m) - 1;
+                    hp = 32 * r + src;
+                    hq = __shfl_sync(0xffffffffu, q, src);
+                }
+            }
+            if (hp >= 0) {
+                int f0 = hp - off, f1 = hq - off;
+                if (f0 < 64) F.lo ^= 1ull << f0; else F.hi ^= 1ull << (f0 - 64);
+                if (f1 < 64) F.lo ^= 1ull << f1; else F.hi ^= 1ull << (f1 - 64);
+                errorbit = f0; nfixed = 2; S = 0;
+            }
+        }
+    }
+    crc = S;
+}
+
+__device__ __forceinline__ void frame_words(U128 F, uint32_t W[4]) {
+    W[0] = __brev((uint32_t)F.lo); W[1] = __brev((uint32_t)(F.lo >> 32));
+    W[2] = __brev((uint32_t)F.hi); W[3] = __brev((uint32_t)(F.hi >> 32)) & 0xffff0000u;
+}
+
+// Slice 112 bits from (lo, hi) half-bit magnitudes held 4 rounds per lane
+// (round r, lane l <-> bit 32r+l), then gate, CRC, repair.
+__device__ __forceinline__ void evaluate_pass(const int lo[4], const int hi[4], uint32_t sum56, uint32_t sum112,
+                                              int fix_errors, int aggressive, const uint32_t *s_syn,
+                                              const uint32_t *s_hash, int lane, PassResult &R) {
+    bool def[4], one[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        int b = 32 * r + lane;
+        int d = lo[r] - hi[r]; d = d < 0 ? -d : d;
+        bool valid = b < 112;
+        def[r] = valid && (b == 0 || d >= 256);              // dump1090.c:1675
+        one[r] = def[r] && lo[r] > hi[r];
+    }
+    U128 D = ballot128(def[0], def[1], def[2], def[3]);
+    U128 O = ballot128(one[0], one[1], one[2], one[3]);
+    uint32_t tri = __ballot_sync(0xffffffffu, lane == 0 && lo[0] == hi[0]) & 1u;   // bits[0] = 2, :1681
+    U128 F = fill128(D, O);
+    if (tri) {
+        // The 2 propagates through the copy bits after bit 0; packed with <<(7-k%8)
+        // each 2 at bit k sets bit k-1 unless k is the first bit of a byte (:1696-1706).
+        U128 T; T.lo = ~D.lo | 1ull; T.hi = ~D.hi;
+        uint64_t t0 = T.lo + 1ull, t1 = T.hi + (t0 == 0 ? 1ull : 0ull);
+        U128 run; run.lo = T.lo & ~t0; run.hi = (t0 == 0) ? (T.hi & ~t1) : 0ull;
+        uint64_t e0 = (run.lo >> 1) | (run.hi << 63), e1 = run.hi >> 1;
+        F.lo |= e0 & 0x7f7f7f7f7f7f7f7full;
+        F.hi |= e1 & 0x7f7f7f7f7f7f7f7full;
+    }
+    F.hi &= 0x0000ffffffffffffull;
+    uint32_t W0 = __brev((uint32_t)F.lo);
+    R.msgtype = W0 >> 27;
+    const int msgbits = (R.msgtype >= 16 && R.msgtype <= 21) ? 112 : 56;      // dump1090.c:746-753
+    uint32_t delta = (msgbits == 112) ? sum112 / 56u : sum56 / 28u;            // :1713-1718
+    R.flags = tri ? MODES_EVAL_ERRORS : 0;
+    R.crc = 0; R.errorbit = 0xFF; R.nfixed = 0;
+    if (delta >= 2550u) {                                                      // :1723
+        R.flags |= MODES_EVAL_GATE_OK;
+        if (!tri || aggressive) {                                              // :1731 (errors is 0 or 1)
+            R.flags |= MODES_EVAL_DECODED;
+            crc_and_fix(F, msgbits, R.msgtype, fix_errors, aggressive, s_syn, s_hash, lane, R.crc, R.errorbit, R.nfixed);
+        }
+    }
+    frame_words(F, R.W);
+}
+
+__device__ __forceinline__ bool unconditionally_good(const PassResult &R) {
+    return (R.flags & MODES_EVAL_DECODED) && R.crc == 0 && (R.msgtype == 11 || R.msgtype == 17 || R.msgtype == 18);
+}
+
+// Word k (0..5) of a modes_frame_eval as laid out in memory.
+__device__ __forceinline__ uint32_t eval_word(const PassResult &R, int k) {
+    switch (k) {
+        case 0: return __byte_perm(R.W[0], 0, 0x0123);
+        case 1: return __byte_perm(R.W[1], 0, 0x0123);
+        case 2: return __byte_perm(R.W[2], 0, 0x0123);
+        case 3: return (R.W[3] >> 24) | ((R.W[3] >> 8) & 0xff00u) | (R.msgtype << 16) | (R.flags << 24);
+        case 4: return R.errorbit | (R.nfixed << 8);
+        default: return R.crc;
+    }
+}
+
+constexpr int kEvalThreads = 256;
+
+__global__ void __launch_bounds__(kEvalThreads)
+eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, const uint32_t *counters,
+            uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
+    __shared__ uint32_t s_syn[112];
+    __shared__ uint32_t s_hash[kFixHashSlots];
+    for (int i = threadIdx.x; i < 112; i += blockDim.x) s_syn[i] = tab.bit_syn[i];
+    for (int i = threadIdx.x; i < kFixHashSlots; i += blockDim.x) s_hash[i] = tab.fix_hash[i];
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps_per_block = kEvalThreads / 32;
+    uint32_t n_cand = counters[0];
+    if (n_cand > cand_capacity) n_cand = cand_capacity;
+
+    for (uint32_t ci = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ci < n_cand;
+         ci += gridDim.x * warps_per_block) {
+        const uint32_t v = cand_v[ci];
+        const uint64_t t = (uint64_t)v - 2;
+
+        // magnitudes: 17 preamble samples m[-1..15] (lane p holds m[p-1]) and 112 (low, high) pairs
+        int pm = 0;
+        if (lane < 17) pm = __ldg(tab.lutn + sample_n(in, (uint64_t)v - 1 + lane));
+        int lo[4], hi[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int b = 32 * r + lane;
+            lo[r] = 0; hi[r] = 0;
+            if (b < 112) {
+                uint64_t s = (uint64_t)v + 16 + 2 * b;
+                lo[r] = __ldg(tab.lutn + sample_n(in, s));
+                hi[r] = __ldg(tab.lutn + sample_n(in, s + 1));
+            }
+        }
+        // sums for the delta gate, on the uncorrected samples (dump1090.c:1692-1693, :1713-1718)
+        uint32_t d56 = 0, d112 = 0;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int d = lo[r] - hi[r]; d = d < 0 ? -d : d;
+            d112 += d;
+            if (32 * r + lane < 56) d56 += d;
+        }
+        d56 = __reduce_add_sync(0xffffffffu, d56);
+        d112 = __reduce_add_sync(0xffffffffu, d112);
+
+        PassResult P1, P2;
+        evaluate_pass(lo, hi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P1);
+        P2.W[0] = P2.W[1] = P2.W[2] = P2.W[3] = 0;
+        P2.msgtype = 0; P2.flags = 0; P2.errorbit = 0; P2.nfixed = 0; P2.crc = 0;
+
+        if ((P1.flags & MODES_EVAL_GATE_OK) && !unconditionally_good(P1)) {
+            P1.flags |= MODES_EVAL_P2_VALID;
+            if ((((uint32_t)t) & (kBufSamples - 1)) == 0) {
+                P2 = P1;                                     // j == 0: retry without correction (:1660)
+                P2.flags &= ~MODES_EVAL_P2_VALID;
+            } else {
+                // applyPhaseCorrection, dump1090.c:1498-1558
+                int m_1 = __shfl_sync(0xffffffffu, pm, 0), m0 = __shfl_sync(0xffffffffu, pm, 1);
+                int m2 = __shfl_sync(0xffffffffu, pm, 3),  m3 = __shfl_sync(0xffffffffu, pm, 4);
+                int m6 = __shfl_sync(0xffffffffu, pm, 7),  m7 = __shfl_sync(0xffffffffu, pm, 8);
+                int m9 = __shfl_sync(0xffffffffu, pm, 10), m10 = __shfl_sync(0xffffffffu, pm, 11);
+                uint32_t on_time = m0 + m2 + m7 + m9;
+                uint32_t early = (uint32_t)(m_1 + m6) * 2u, late = (uint32_t)(m3 + m10) * 2u;
+                int clo[4], chi[4];
+                if (early > late) {
+                    // walk backwards: only the second half-bit samples are rescaled
+                    uint32_t q = 16384u * early / (early + on_time);
+                    int up = (int)((16384u + q) & 0xffffu), down = (int)((16384u - q) & 0xffffu);
+                    int hu[4], hd[4];
+                    bool def[4], one[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        int b = 32 * r + lane;
+                        hu[r] = scale_sample(hi[r], up); hd[r] = scale_sample(hi[r], down);
+                        bool g0 = lo[r] > hu[r], g1 = lo[r] > hd[r];        // decision if the bit above was 0 / 1
+                        def[r] = b < 112 && (b == 111 || g0 == g1);
+                        one[r] = def[r] && g0;
+                    }
+                    U128 D = rev112(ballot128(def[0], def[1], def[2], def[3]));
+                    U128 O = rev112(ballot128(one[0], one[1], one[2], one[3]));
+                    D.hi |= 0xffff000000000000ull;                          // padding: definite zeros
+                    U128 E = fill128(D, O);                                 // E bit (111-b) = decision at bit b
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        int b = 32 * r + lane;
+                        clo[r] = lo[r];
+                        chi[r] = hi[r];
+                        if (b == 111) chi[r] = hu[r];
+                        else if (b < 111) chi[r] = bit_of(E, 110 - b) ? hd[r] : hu[r];
+                    }
+                } else {
+                    // walk forwards: only the first half-bit samples are rescaled
+                    uint32_t q = 16384u * late / (late + on_time);
+                    int up = (int)((16384u + q) & 0xffffu), down = (int)((16384u - q) & 0xffffu);
+                    int lu[4], ld[4];
+                    bool def[4], one[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        int b = 32 * r + lane;
+                        lu[r] = scale_sample(lo[r], up); ld[r] = scale_sample(lo[r], down);
+                        bool f1 = lu[r] > hi[r], f0 = ld[r] > hi[r];        // decision if the bit below was 1 / 0
+                        def[r] = b < 112 && (b == 0 || f0 == f1);
+                        one[r] = def[r] && f1;
+                    }
+                    U128 D = ballot128(def[0], def[1], def[2], def[3]);
+                    U128 O = ballot128(one[0], one[1], one[2], one[3]);
+                    U128 E = fill128(D, O);                                 // E bit b = decision at bit b
+#pragma unroll
+                    for (int r = 0; r < 4; r++) {
+                        int b = 32 * r + lane;
+                        chi[r] = hi[r];
+                        clo[r] = lo[r];
+                        if (b == 0) clo[r] = lu[r];
+                        else if (b < 112) clo[r] = bit_of(E, b - 1) ? lu[r] : ld[r];
+                    }
+                }
+                evaluate_pass(clo, chi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P2);
+            }
+        }
+
+        // one coalesced 56-byte record: lanes 0..13 write one word each
+        uint32_t word;
+        if (lane == 0) word = (uint32_t)t;
+        else if (lane == 1) word = (uint32_t)(t >> 32);
+        else if (lane < 8) word = eval_word(P1, lane - 2);
+        else word = eval_word(P2, lane - 8);
+        if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = word;
+    }
+}
+
+void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
+                 modes_candidate *records, int fix_errors, int aggressive, int sm_count,
+                 cudaStream_t stream) {
+    eval_kernel<<<sm_count * 4, kEvalThreads, 0, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
+                                                          records, fix_errors, aggressive);
+}
+
+// ------------------------------------------------------- magnitude (tests)
+
+__global__ void __launch_bounds__(256)
+magnitude_kernel(const uint8_t *__restrict__ iq, uint16_t *__restrict__ mag, uint64_t n_samples,
+                 const uint16_t *__restrict__ lutn) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; i < n_samples; i += stride) {
+        uint32_t w = reinterpret_cast<const uint16_t *>(iq)[i];
+        uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
+        mag[i] = __ldg(lutn + __dp4a(a, a, 0u));
+    }
+}
+
+void launch_magnitude(const uint8_t *d_iq, uint16_t *d_mag, uint64_t n_samples, const uint16_t *lutn,
+                      cudaStream_t stream) {
+    if (!n_samples) return;
+    uint64_t blocks = (n_samples + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    magnitude_kernel<<<(uint32_t)blocks, 256, 0, stream>>>(d_iq, d_mag, n_samples, lutn);
+}
+
+// ------------------------------------------------------- hex door
+
+__global__ void __launch_bounds__(32)
+eval_frames_kernel(const uint8_t *__restrict__ frames, modes_frame_eval *out, uint32_t n, DeviceTables tab,
+                   int fix_errors, int aggressive) {
+    __shared__ uint32_t s_syn[112];
+    __shared__ uint32_t s_hash[kFixHashSlots];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < 112; i += 32) s_syn[i] = tab.bit_syn[i];
+    for (int i = lane; i < kFixHashSlots; i += 32) s_hash[i] = tab.fix_hash[i];
+    __syncwarp();
+    for (uint32_t f = blockIdx.x; f < n; f += gridDim.x) {
+        const uint8_t *m = frames + 14 * (size_t)f;
+        // frame bit b lives at bit b of F
+        bool bit[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            int b = 32 * r + lane;
+            bit[r] = b < 112 && ((m[b >> 3] >> (7 - (b & 7))) & 1);
+        }
+        U128 F = ballot128(bit[0], bit[1], bit[2], bit[3]);
+        PassResult R;
+        R.msgtype = m[0] >> 3;
+        const int msgbits = (R.msgtype >= 16 && R.msgtype <= 21) ? 112 : 56;
+        R.flags = MODES_EVAL_GATE_OK | MODES_EVAL_DECODED;
+        crc_and_fix(F, msgbits, R.msgtype, fix_errors, aggressive, s_syn, s_hash, lane, R.crc, R.errorbit, R.nfixed);
+        frame_words(F, R.W);
+        if (lane < 6) reinterpret_cast<uint32_t *>(out + f)[lane] = eval_word(R, lane);
+    }
+}
+
+void launch_eval_frames(const uint8_t *d_frames, modes_frame_eval *d_out, uint32_t n, const DeviceTables &tab,
+                        int fix_errors, int aggressive, cudaStream_t stream) {
+    if (!n) return;
+    eval_frames_kernel<<<n < 1024 ? n : 1024, 32, 0, stream>>>(d_frames, d_out, n, tab, fix_errors, aggressive);
+}
+
+}  // namespace modes

@@ -1,0 +1,204 @@
+// modes_resolve.cpp — the sequential half of detectModeS(), on the host.
+//
+// The device evaluates every preamble position independently; what is left is
+// the reference's order-dependent control flow, replayed over the candidates in
+// stream order:
+//   * retry with phase correction when the first attempt is not a good message,
+//     skip past a good one (dump1090.c:1769-1791); state restarts at every
+//     131072-sample buffer (:1593, :2986)
+//   * ICAO address cache: filled by clean DF11/17/18, consulted by the
+//     address/parity formats and by DF11 with a small residual
+//     (dump1090.c:898-983, :1183-1210)
+//   * statistics (dump1090.c:1651, :1662, :1738-1753, :1122-1126)
+//   * the sink gate (dump1090.c:1803) and struct modesMessage field decode
+//     (:1133-1179, :1212-1308) for delivered messages
+#include <cmath>
+#include <cstring>
+#include "modes_internal.h"
+
+namespace modes {
+
+void ResolveState::reset() {
+    std::memset(icao, 0, sizeof(icao));
+    std::memset(stats, 0, sizeof(stats));
+    cur_buffer = -1;
+    next_j = 0;
+}
+
+static inline uint32_t icao_slot(uint32_t a) {           // dump1090.c:898-905
+    a = ((a >> 16) ^ a) * 0x45d9f3bu;
+    a = ((a >> 16) ^ a) * 0x45d9f3bu;
+    a = (a >> 16) ^ a;
+    return a & 1023u;
+}
+
+static inline bool icao_seen(const ResolveState &st, uint32_t a) {
+    return a != 0 && st.icao[icao_slot(a)] == a;         // dump1090.c:919-925, TTL not modelled
+}
+
+static inline int bits_by_type(int df) { return (df >= 16 && df <= 21) ? 112 : 56; }
+
+// struct modesMessage fields that are pure functions of the frame bytes.
+static void decode_fields(modes_message *o) {
+    static const char ais[] = "?ABCDEFGHIJKLMNOPQRSTUVWXYZ????? ???????????????0123456789??????";
+    const uint8_t *m = o->msg;
+    o->ca = m[0] & 7;
+    o->aa1 = m[1]; o->aa2 = m[2]; o->aa3 = m[3];
+    o->metype = m[4] >> 3; o->mesub = m[4] & 7;
+    o->fs = m[0] & 7;
+    o->dr = (m[1] >> 3) & 31;
+    o->um = ((m[1] & 7) << 3) | (m[2] >> 5);
+    // squawk: C1 A1 C2 A2 C4 A4 0 B1 D1 B2 D2 B4 D4, four octal digits read as decimal
+    {
+        int A = ((m[3] & 0x80) >> 5) | (m[2] & 0x02) | ((m[2] & 0x08) >> 3);
+        int B = ((m[3] & 0x02) << 1) | ((m[3] & 0x08) >> 2) | ((m[3] & 0x20) >> 5);
+        int C = ((m[2] & 0x01) << 2) | ((m[2] & 0x04) >> 1) | ((m[2] & 0x10) >> 4);
+        int D = ((m[3] & 0x01) << 2) | ((m[3] & 0x04) >> 1) | ((m[3] & 0x10) >> 4);
+        o->identity = A * 1000 + B * 100 + C * 10 + D;
+    }
+    const int df = o->msgtype;
+    if (df == 0 || df == 4 || df == 16 || df == 20) {     // 13-bit altitude code
+        o->altitude = 0;
+        if (m[3] & 0x40) {
+            o->unit = 1;                                   // metres: not decoded by the reference
+        } else {
+            o->unit = 0;
+            if (m[3] & 0x10) {
+                int n = ((m[2] & 31) << 6) | ((m[3] & 0x80) >> 2) | ((m[3] & 0x20) >> 1) | (m[3] & 15);
+                o->altitude = n * 25 - 1000;
+            }
+        }
+    }
+    if (df != 17 && df != 18) return;
+    const int tc = o->metype, sub = o->mesub;
+    if (tc >= 1 && tc <= 4) {
+        o->aircraft_type = tc - 1;
+        const uint32_t hi = ((uint32_t)m[5] << 16) | ((uint32_t)m[6] << 8) | m[7];
+        const uint32_t lo = ((uint32_t)m[8] << 16) | ((uint32_t)m[9] << 8) | m[10];
+        for (int k = 0; k < 4; k++) {
+            o->flight[k] = ais[(hi >> (18 - 6 * k)) & 63];
+            o->flight[4 + k] = ais[(lo >> (18 - 6 * k)) & 63];
+        }
+        o->flight[8] = 0;
+    } else if (tc >= 5 && tc <= 8) {
+        o->movement = ((m[4] & 7) << 4) | (m[5] >> 4);
+        o->movement_valid = o->movement != 0;
+        o->ground_track_valid = (m[5] >> 3) & 1;
+        o->ground_track = (((m[5] & 7) << 4) | (m[6] >> 4)) * 360 / 128;
+        o->fflag = (m[6] >> 2) & 1;
+        o->tflag = (m[6] >> 3) & 1;
+        o->raw_latitude = ((m[6] & 3) << 15) | (m[7] << 7) | (m[8] >> 1);
+        o->raw_longitude = ((m[8] & 1) << 16) | (m[9] << 8) | m[10];
+    } else if (tc >= 9 && tc <= 18) {
+        o->fflag = m[6] & 4;                               // the reference keeps the mask value here
+        o->tflag = m[6] & 8;
+        o->altitude = 0;
+        if (m[5] & 1) {
+            o->unit = 0;
+            o->altitude = (((m[5] >> 1) << 4) | (m[6] >> 4)) * 25 - 1000;
+        }
+        o->raw_latitude = ((m[6] & 3) << 15) | (m[7] << 7) | (m[8] >> 1);
+        o->raw_longitude = ((m[8] & 1) << 16) | (m[9] << 8) | m[10];
+    } else if (tc == 19 && sub >= 1 && sub <= 4) {
+        if (sub <= 2) {
+            o->ew_dir = (m[5] >> 2) & 1;
+            o->ew_velocity = ((m[5] & 3) << 8) | m[6];
+            o->ns_dir = m[7] >> 7;
+            o->ns_velocity = ((m[7] & 0x7f) << 3) | (m[8] >> 5);
+            o->vert_rate_source = (m[8] >> 4) & 1;
+            o->vert_rate_sign = (m[8] >> 3) & 1;
+            o->vert_rate = ((m[8] & 7) << 6) | (m[9] >> 2);
+            o->velocity = (int)std::sqrt((double)(o->ns_velocity * o->ns_velocity + o->ew_velocity * o->ew_velocity));
+            o->heading = 0;
+            if (o->velocity) {
+                int ewv = o->ew_dir ? -o->ew_velocity : o->ew_velocity;
+                int nsv = o->ns_dir ? -o->ns_velocity : o->ns_velocity;
+                double h = std::atan2((double)ewv, (double)nsv);
+                o->heading = (int)(h * 360 / (M_PI * 2));
+                if (o->heading < 0) o->heading += 360;
+            }
+        } else {
+            o->heading_is_valid = m[5] & 4;
+            o->heading = (int)((360.0 / 128) * (((m[5] & 3) << 5) | (m[6] >> 3)));
+        }
+    }
+}
+
+int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *o) {
+    std::memset(o, 0, sizeof(*o));
+    std::memcpy(o->msg, p.msg, 14);
+    o->msgtype = p.msgtype;
+    o->msgbits = bits_by_type(p.msgtype);
+    o->crc = p.crc;
+    o->nfixed = p.nfixed;
+    o->errorbit = p.nfixed ? (int)p.errorbit : -1;
+    o->crcok = p.crc == 0;
+    if (p.nfixed == 1) st.stats[6]++;                      // dump1090.c:1122-1126
+    else if (p.nfixed == 2) st.stats[7]++;
+    decode_fields(o);
+    const int df = o->msgtype;
+    if (df == 11 || df == 17 || df == 18) {
+        const uint32_t addr = ((uint32_t)o->aa1 << 16) | ((uint32_t)o->aa2 << 8) | (uint32_t)o->aa3;
+        if (o->crcok && o->errorbit == -1) st.icao[icao_slot(addr)] = addr;
+        if (df == 11 && !o->crcok && o->crc < 80 && icao_seen(st, addr)) {
+            o->iid = (int32_t)o->crc;
+            o->crcok = 1;
+        }
+    } else {
+        o->crcok = 0;
+        if (df == 0 || df == 4 || df == 5 || df == 16 || df == 20 || df == 21 || df == 24) {
+            // parity field = CRC ^ address, so the syndrome is the sender's address
+            const uint32_t addr = p.crc;
+            if (icao_seen(st, addr)) {
+                o->aa1 = (addr >> 16) & 0xff; o->aa2 = (addr >> 8) & 0xff; o->aa3 = addr & 0xff;
+                o->crcok = 1;
+            }
+        }
+    }
+    return o->crcok;
+}
+
+// One evaluated attempt, as detectModeS handles it after the delta gate.
+// Returns true when the message is good (the scan skips past it).
+static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const modes_frame_eval &p, bool retry,
+                           int64_t sample_pos, modes_sink_fn sink, void *user) {
+    if (!(p.flags & MODES_EVAL_DECODED)) return false;
+    modes_message mm;
+    const int crcok = finish_message(st, p, &mm);
+    if (crcok || retry) {                                  // dump1090.c:1738-1753
+        if (!(p.flags & MODES_EVAL_ERRORS)) st.stats[2]++;
+        if (mm.errorbit == -1) st.stats[crcok ? 3 : 4]++;
+        else { st.stats[4]++; st.stats[5]++; st.stats[6]++; }
+    }
+    mm.sample_pos = sample_pos;
+    if (crcok && retry) mm.phase_corrected = 1;            // dump1090.c:1772-1773
+    if (sink && (cfg.check_crc == 0 || crcok)) sink(user, &mm);
+    return crcok != 0;
+}
+
+void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base,
+                        modes_sink_fn sink, void *user) {
+    for (size_t ti = 0; ti < n_tiles; ti++) {
+        const modes_candidate *c = cands + tiles[ti].offset;
+        for (uint32_t k = 0; k < tiles[ti].count; k++, c++) {
+            const int64_t buffer = buffer_base + (c->t >> 17);
+            const uint32_t j = (uint32_t)(c->t & (kBufSamples - 1));
+            if (buffer != st.cur_buffer) { st.cur_buffer = buffer; st.next_j = 0; }
+            if (j < st.next_j) continue;                   // inside a message already taken
+            st.stats[0]++;                                 // dump1090.c:1651
+            const modes_frame_eval &p1 = c->pass[0];
+            if (!(p1.flags & MODES_EVAL_GATE_OK)) continue;        // dump1090.c:1723-1726
+            const int64_t pos = buffer * (int64_t)kBufSamples + j - MODES_CARRY_SAMPLES;
+            const uint32_t skip = (uint32_t)(8 + bits_by_type(p1.msgtype)) * 2 + 1;
+            if (attempt(st, cfg, p1, false, pos, sink, user)) { st.next_j = j + skip; continue; }
+            if (j) st.stats[1]++;                          // dump1090.c:1660-1663
+            const modes_frame_eval &p2 = c->pass[1];
+            if (!(p2.flags & MODES_EVAL_GATE_OK)) continue;
+            const uint32_t skip2 = (uint32_t)(8 + bits_by_type(p2.msgtype)) * 2 + 1;
+            if (attempt(st, cfg, p2, true, pos, sink, user)) st.next_j = j + skip2;
+        }
+    }
+}
+
+}  // namespace modes

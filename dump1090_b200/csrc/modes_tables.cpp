@@ -1,0 +1,47 @@
+// modes_tables.cpp — host-side construction of the small constant tables the
+// kernels read.  Generated from their defining formulas, never copied:
+//   lutn     magnitude by squared amplitude: the reference's
+//            round(sqrt(i*i+q*q)*360) (dump1090.c:362) keyed by n = i*i+q*q
+//   bit_syn  syndrome of one flipped bit at frame position p of a 112-bit frame:
+//            x^(111-p) mod the Mode S generator 0x1FFF409 for data bits (what
+//            modes_checksum_table holds, dump1090.c:683-698), the bit itself for
+//            the 24 parity bits (dump1090.c:738-741)
+//   fix_hash open-addressed inverse of bit_syn over positions 5..111, the domain
+//            of the reference's bitErrorTable (dump1090.c:806)
+#include <cmath>
+#include <cstring>
+#include "modes_internal.h"
+
+namespace modes {
+
+void build_lutn(uint16_t *out) {
+    for (int n = 0; n < kNLutEntries; n++) out[n] = (uint16_t)std::round(std::sqrt((double)n) * 360);
+}
+
+void build_bit_syndromes(uint32_t *out) {
+    uint32_t v = 0xFFF409;                       // x^24 mod G
+    for (int p = 87; p >= 0; p--) {
+        out[p] = v;
+        v <<= 1;
+        if (v & 0x1000000u) v ^= 0x1FFF409u;
+    }
+    for (int p = 88; p < 112; p++) out[p] = 1u << (111 - p);
+}
+
+bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out) {
+    std::memset(out, 0xFF, sizeof(uint32_t) * kFixHashSlots);
+    for (int p = 5; p < 112; p++) {
+        uint32_t s = bit_syn[p];
+        uint32_t h = (s * 0x9E3779B1u) >> 24;
+        int i = 0;
+        for (; i < kFixHashSlots; i++) {
+            uint32_t &e = out[(h + i) & (kFixHashSlots - 1)];
+            if (e == 0xFFFFFFFFu) { e = (s << 8) | (uint32_t)p; break; }
+            if ((e >> 8) == s) return false;     // two positions with one syndrome: impossible for this code
+        }
+        if (i == kFixHashSlots) return false;
+    }
+    return true;
+}
+
+}  // namespace modes

@@ -1,0 +1,193 @@
+/* modes_b200.h — C ABI of the B200-native Mode S / ADS-B demodulator.
+ *
+ * Drop-in boundary for dump1090's --ifile decode path.  The reference has no
+ * plugin/FFI surface; the seam is its main loop (dump1090.c:2968-2990):
+ *
+ *     computeMagnitudeVector();                       dump1090.c:1454 / :2974
+ *     detectModeS(Modes.magnitude, Modes.data_len/2); dump1090.c:1563 / :2986
+ *         -> decodeModesMessage(&mm, msg)             dump1090.c:1091 / :1735
+ *         -> useModesMessage(&mm)                     dump1090.c:1802 / :1777
+ *
+ * Each entry point below names the reference interface it replaces.  Plain C
+ * types only; the library owns all device memory, streams and chunking, so
+ * a caller passes raw file bytes in file order in pieces of any size and gets
+ * back, in stream order, exactly the messages (and struct modesMessage fields)
+ * the reference hands to useModesMessage() for the same bytes.
+ *
+ * There is no CPU fallback: modes_create() fails (NULL + modes_last_error)
+ * when no CUDA device is usable.
+ */
+#ifndef MODES_B200_H
+#define MODES_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MODES_B200_ABI_VERSION 1
+
+/* Sizes fixed by the reference's buffering (dump1090.c:54, :61, :331). */
+#define MODES_BUFFER_BYTES    262144      /* MODES_DATA_LEN: new bytes per reference buffer */
+#define MODES_BUFFER_SAMPLES  131072
+#define MODES_CARRY_BYTES     476         /* (MODES_FULL_LEN-1)*4 carried into the next buffer */
+#define MODES_CARRY_SAMPLES   238
+
+/* Replaces the four globals that change hot-path results: Modes.fix_errors
+ * (dump1090.c:167, --no-fix :2873), Modes.aggressive (:179, :2896),
+ * Modes.check_crc (:168, :2875), plus the EOF-buffer race made explicit
+ * (dump1090.c:497 vs :2989). */
+typedef struct modes_config {
+    int32_t fix_errors;         /* 1 (default): 1-bit (2-bit if aggressive) CRC repair on DF11/17/18 */
+    int32_t aggressive;         /* 0 (default) */
+    int32_t check_crc;          /* 1 (default): deliver only messages with crcok */
+    int32_t drop_eof_buffer;    /* 0 (default): decode the buffer that hit EOF; 1: drop it, as the
+                                   stock binary does in most runs */
+    int32_t device;             /* CUDA device ordinal, default 0 */
+    int32_t profile;            /* 1: record per-kernel CUDA-event times (modes_get_kernel_times) */
+    uint64_t max_batch_bytes;   /* device staging per in-flight batch; 0 = 256 MiB */
+} modes_config;
+
+/* Replaces struct modesMessage (dump1090.c:211-260): same field names and
+ * meaning, 32-bit fields in a fixed order.  Fields the reference leaves
+ * unassigned for a given DF are 0 here.  nfixed and sample_pos are additions. */
+typedef struct modes_message {
+    uint8_t  msg[14];
+    uint8_t  pad0[2];
+    int32_t  msgbits, msgtype, crcok;
+    uint32_t crc;
+    int32_t  errorbit, aa1, aa2, aa3, phase_corrected;
+    int32_t  ca, iid;
+    int32_t  metype, mesub, heading_is_valid, heading, aircraft_type;
+    int32_t  fflag, tflag, raw_latitude, raw_longitude;
+    char     flight[9];
+    char     pad1[3];
+    int32_t  ew_dir, ew_velocity, ns_dir, ns_velocity;
+    int32_t  vert_rate_source, vert_rate_sign, vert_rate, velocity;
+    int32_t  movement, movement_valid, ground_track, ground_track_valid;
+    int32_t  fs, dr, um, identity;
+    int32_t  altitude, unit;
+    int32_t  nfixed;            /* bits repaired by the CRC fix (0/1/2) */
+    int32_t  pad2;
+    int64_t  sample_pos;        /* stream sample index of the preamble start */
+} modes_message;
+
+/* One evaluated frame attempt at one preamble position: everything
+ * detectModeS()+decodeModesMessage() compute that is a pure function of the
+ * samples and the flags (dump1090.c:1668-1735, :1099-1128). */
+typedef struct modes_frame_eval {
+    uint8_t  msg[14];           /* frame bytes, after the CRC fix if one was applied */
+    uint8_t  msgtype;           /* DF of the demodulated frame (before any fix) */
+    uint8_t  flags;             /* MODES_EVAL_* */
+    uint8_t  errorbit;          /* first repaired bit, 0xFF = none */
+    uint8_t  nfixed;
+    uint32_t crc;               /* 24-bit syndrome after the fix; 0 when not decoded */
+} modes_frame_eval;
+
+#define MODES_EVAL_GATE_OK   1  /* mean |low-high| >= 2550             dump1090.c:1723 */
+#define MODES_EVAL_ERRORS    2  /* demodulation error in first 56 bits dump1090.c:1682 */
+#define MODES_EVAL_DECODED   4  /* decodeModesMessage reached          dump1090.c:1731 */
+#define MODES_EVAL_P2_VALID  8  /* pass[1] (phase-corrected retry) was evaluated */
+
+/* One preamble candidate: a position that passes the tests of
+ * dump1090.c:1602-1650, with the first attempt and the phase-corrected retry
+ * (dump1090.c:1653-1664) both evaluated on the device. */
+typedef struct modes_candidate {
+    int64_t t;                  /* 131072*buffer_index + j  (j = index inside the reference buffer) */
+    modes_frame_eval pass[2];
+} modes_candidate;
+
+/* Per scan tile: where its candidates sit in the candidate array.  Tiles are
+ * in stream order; candidates inside a tile are in stream order. */
+typedef struct modes_tile { uint32_t offset, count; } modes_tile;
+#define MODES_TILE_SAMPLES 2048
+
+/* Replaces Modes.stat_* (dump1090.c:186-195) in the order the reference prints
+ * them (:2994-3003): valid_preamble, out_of_phase, demodulated, goodcrc,
+ * badcrc, fixed, single_bit_fix, two_bits_fix. */
+typedef struct modes_stats { int64_t v[8]; } modes_stats;
+
+typedef struct modes_ctx modes_ctx;
+
+/* Replaces useModesMessage(struct modesMessage*) (dump1090.c:1802): called on
+ * the calling thread from modes_process/modes_finish/modes_resolve, in stream
+ * order, once per message that passes the reference's gate (:1803).  The
+ * pointer is valid only during the call. */
+typedef void (*modes_sink_fn)(void *user, const modes_message *mm);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int         modes_abi_version(void);
+void        modes_default_config(modes_config *cfg);                 /* modesInitConfig, dump1090.c:299 */
+modes_ctx  *modes_create(const modes_config *cfg);                   /* modesInit, dump1090.c:321 */
+void        modes_destroy(modes_ctx *ctx);
+const char *modes_last_error(const modes_ctx *ctx);                  /* ctx may be NULL: create() error */
+int         modes_set_sink(modes_ctx *ctx, modes_sink_fn fn, void *user);
+
+/* ---- streaming decode: the main loop, dump1090.c:2968-2990 -------------- */
+/* Feed the next `nbytes` of the u8 I/Q stream (host memory, pinned or not).
+ * Whole reference buffers are decoded as they complete.  0 = ok, <0 = error. */
+int  modes_process(modes_ctx *ctx, const uint8_t *iq, size_t nbytes);
+/* End of stream: 127-pad and decode (or drop) the EOF buffer (dump1090.c:496-507). */
+int  modes_finish(modes_ctx *ctx);
+/* Forget stream position, carry, ICAO cache and statistics (a new --ifile run). */
+int  modes_reset(modes_ctx *ctx);
+int  modes_get_stats(const modes_ctx *ctx, modes_stats *out);
+
+/* ---- stage-level entry points (tests, bench, multi-GPU sharding) -------- */
+/* computeMagnitudeVector() alone (dump1090.c:1454-1469): nsamples I/Q pairs in
+ * host memory -> nsamples u16 magnitudes in host memory, computed on the device. */
+int  modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples, uint16_t *mag);
+
+/* The device half of detectModeS() on data already in HBM.  d_iq: n_buffers *
+ * MODES_BUFFER_BYTES bytes of device memory (16-byte aligned) holding whole
+ * reference buffers of the stream; carry476: the MODES_CARRY_BYTES stream
+ * bytes preceding d_iq (host memory), or NULL at stream start (no-signal).
+ * Launches the scan and frame-evaluation kernels on the context's stream and
+ * returns without waiting.  d_candidates (capacity cand_capacity records) and
+ * d_tiles (n_buffers*64+1 entries) are device memory supplied by the caller, or
+ * NULL to use the context's own workspace. */
+int  modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, const uint8_t *carry476,
+                         void *d_candidates, size_t cand_capacity, void *d_tiles);
+/* Wait for the last modes_detect_device; returns the candidate count. */
+int  modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates);
+/* Copy the last result to host memory (arrays sized by the caller from
+ * modes_detect_wait's count and n_buffers*64+1 tiles). */
+int  modes_detect_fetch(modes_ctx *ctx, modes_candidate *candidates, modes_tile *tiles);
+
+/* The sequential half of detectModeS(): retry/skip state machine
+ * (dump1090.c:1769-1791), ICAO cache (:898-983, :1183-1210), statistics and the
+ * sink gate (:1803), replayed over candidates in stream order.  buffer_base is
+ * the stream index of the first reference buffer the arrays describe. */
+int  modes_resolve(modes_ctx *ctx, const modes_candidate *candidates, const modes_tile *tiles,
+                   size_t n_tiles, int64_t buffer_base);
+
+/* The same sequential half as a standalone host object (no device needed): what
+ * rank 0 runs over gathered candidate records in a multi-GPU job. */
+typedef struct modes_resolver modes_resolver;
+modes_resolver *modes_resolver_create(const modes_config *cfg);
+void modes_resolver_destroy(modes_resolver *r);
+int  modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                        size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user);
+int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
+
+/* decodeModesMessage() on frame bytes (the reference's hex door,
+ * decodeHexMessage dump1090.c:2472-2502): CRC, fix and field decode run on the
+ * device + resolve path with the context's ICAO cache. */
+int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out);
+
+/* ---- plumbing ----------------------------------------------------------- */
+void *modes_stream(modes_ctx *ctx);                    /* the context's cudaStream_t */
+void *modes_host_alloc(size_t nbytes);                 /* pinned host memory for modes_process input */
+void  modes_host_free(void *p);
+/* ms of the last batch per kernel when cfg.profile: [0] scan (magnitude+preamble),
+ * [1] frame evaluation, [2] whole device batch, [3] launches in the batch. */
+int  modes_get_kernel_times(const modes_ctx *ctx, float ms[4]);
+/* Cumulative count of kernel launches issued by this context. */
+uint64_t modes_launch_count(const modes_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODES_B200_H */
