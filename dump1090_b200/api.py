@@ -94,7 +94,8 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_stats", "modes_decode_frame", "modes_stream", "modes_host_alloc",
+           "modes_resolver_stats", "modes_decode_frame", "modes_stream", "modes_set_stream",
+           "modes_set_output", "modes_output_count", "modes_host_alloc",
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
 
 
@@ -130,6 +131,10 @@ def lib():
         L.modes_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Message)]
         L.modes_stream.restype = C.c_void_p
         L.modes_stream.argtypes = [C.c_void_p]
+        L.modes_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.modes_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_output_count.restype = C.c_size_t
+        L.modes_output_count.argtypes = [C.c_void_p]
         L.modes_host_alloc.restype = C.c_void_p
         L.modes_host_alloc.argtypes = [C.c_size_t]
         L.modes_host_free.argtypes = [C.c_void_p]
@@ -258,6 +263,28 @@ class Decoder:
             self.process(a)
         self.finish()
         return self.take_messages()
+
+    def set_output_array(self, capacity: int):
+        """Deliver messages into a preallocated array instead of the Python callback
+        (no per-message interpreter work).  Returns the ctypes array; capacity 0 restores the callback."""
+        if capacity <= 0:
+            self._out = None
+            lib().modes_set_output(self._h, None, 0)
+            lib().modes_set_sink(self._h, self._collector.fn, None)
+            return None
+        self._out = (Message * capacity)()
+        lib().modes_set_sink(self._h, C.cast(None, SINK_FN), None)
+        lib().modes_set_output(self._h, self._out, capacity)
+        return self._out
+
+    def rearm_output(self) -> None:
+        lib().modes_set_output(self._h, self._out, len(self._out))
+
+    def output_count(self) -> int:
+        return int(lib().modes_output_count(self._h))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        self._check(lib().modes_set_stream(self._h, C.c_void_p(cuda_stream)))
 
     def stats(self) -> dict:
         st = Stats()

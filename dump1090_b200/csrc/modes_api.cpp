@@ -63,9 +63,18 @@ struct modes_ctx {
     ResolveState rs;
     modes_sink_fn sink = nullptr;
     void *sink_user = nullptr;
+    modes_sink_fn user_sink = nullptr;    // what the caller registered
+    void *user_sink_user = nullptr;
+    modes_message *out_buf = nullptr;     // modes_set_output
+    size_t out_cap = 0, out_n = 0;
+    cudaStream_t own_detect_stream = nullptr;
     std::string err;
     uint64_t launches = 0;
-    float times[4] = {0, 0, 0, 0};
+    // cfg.profile: ring of CUDA-event triplets, one per batch, recorded on the launching stream
+    static constexpr int kProfRing = 512;
+    cudaEvent_t prof_ev[kProfRing][3];
+    bool prof_ready = false;
+    uint64_t prof_head = 0, prof_tail = 0;   // batches recorded / batches already reported
 };
 
 namespace {
@@ -174,11 +183,21 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
     s.out_cap = d_records_ext ? (cap_ext < s.cand_cap ? cap_ext : s.cand_cap) : s.cand_cap;
     ScanOutputs so{s.d_cand_v, s.out_cap, s.out_tiles, s.d_counters};
 
-    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[0], s.stream));
+    cudaEvent_t *pe = nullptr;
+    if (ctx->cfg.profile) {
+        if (!ctx->prof_ready) {
+            for (auto &trip : ctx->prof_ev) for (auto &e : trip) CK(ctx, cudaEventCreate(&e));
+            ctx->prof_ready = true;
+        }
+        if (ctx->prof_head - ctx->prof_tail >= (uint64_t)modes_ctx::kProfRing) ctx->prof_tail = ctx->prof_head - modes_ctx::kProfRing + 1;
+        pe = ctx->prof_ev[ctx->prof_head % modes_ctx::kProfRing];
+        ctx->prof_head++;
+    }
+    if (pe) CK(ctx, cudaEventRecord(pe[0], s.stream));
     launch_scan(in, ctx->tab, so, ctx->sm_count, s.stream);
-    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[1], s.stream));
+    if (pe) CK(ctx, cudaEventRecord(pe[1], s.stream));
     launch_eval(in, ctx->tab, so, s.out_records, ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->sm_count, s.stream);
-    if (ctx->cfg.profile) CK(ctx, cudaEventRecord(s.ev[2], s.stream));
+    if (pe) CK(ctx, cudaEventRecord(pe[2], s.stream));
     CK(ctx, cudaGetLastError());
     ctx->launches += 2;
     CK(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
@@ -191,12 +210,6 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
 // Wait for the slot's batch; returns the number of candidates stored.
 int wait_batch(modes_ctx *ctx, Slot &s, uint64_t *n_out) {
     CK(ctx, cudaEventSynchronize(s.ev[3]));
-    if (ctx->cfg.profile) {
-        cudaEventElapsedTime(&ctx->times[0], s.ev[0], s.ev[1]);
-        cudaEventElapsedTime(&ctx->times[1], s.ev[1], s.ev[2]);
-        cudaEventElapsedTime(&ctx->times[2], s.ev[0], s.ev[2]);
-        ctx->times[3] = 2.0f;
-    }
     if (s.h_counters[1] || s.h_counters[0] > s.out_cap)
         return fail(ctx, "candidate capacity exceeded: %u found, room for %u", s.h_counters[0], s.out_cap);
     *n_out = s.h_counters[0];
@@ -266,8 +279,10 @@ const char *modes_last_error(const modes_ctx *ctx) { return ctx ? ctx->err.c_str
 void modes_destroy(modes_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
+    if (ctx->own_detect_stream) { cudaStreamSynchronize(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
     cudaFree(ctx->d_lutn); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
+    if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
     delete ctx;
 }
@@ -314,9 +329,41 @@ modes_ctx *modes_create(const modes_config *cfg) {
     return ctx;
 }
 
+static void tee_sink(void *user, const modes_message *mm) {
+    modes_ctx *ctx = static_cast<modes_ctx *>(user);
+    if (ctx->out_buf && ctx->out_n < ctx->out_cap) ctx->out_buf[ctx->out_n] = *mm;
+    ctx->out_n++;
+    if (ctx->user_sink) ctx->user_sink(ctx->user_sink_user, mm);
+}
+
+static void rewire_sink(modes_ctx *ctx) {
+    if (ctx->out_buf) { ctx->sink = tee_sink; ctx->sink_user = ctx; }
+    else { ctx->sink = ctx->user_sink; ctx->sink_user = ctx->user_sink_user; }
+}
+
 int modes_set_sink(modes_ctx *ctx, modes_sink_fn fn, void *user) {
     if (!ctx) return -1;
-    ctx->sink = fn; ctx->sink_user = user;
+    ctx->user_sink = fn; ctx->user_sink_user = user;
+    rewire_sink(ctx);
+    return 0;
+}
+
+int modes_set_output(modes_ctx *ctx, modes_message *out, size_t capacity) {
+    if (!ctx) return -1;
+    ctx->out_buf = capacity ? out : nullptr;
+    ctx->out_cap = out ? capacity : 0;
+    ctx->out_n = 0;
+    rewire_sink(ctx);
+    return 0;
+}
+
+size_t modes_output_count(const modes_ctx *ctx) { return ctx ? ctx->out_n : 0; }
+
+int modes_set_stream(modes_ctx *ctx, void *cuda_stream) {
+    if (!ctx) return -1;
+    if (ctx->detect.busy) cudaStreamSynchronize(ctx->detect.stream);
+    if (!ctx->own_detect_stream) ctx->own_detect_stream = ctx->detect.stream;
+    ctx->detect.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_detect_stream;
     return 0;
 }
 
@@ -485,9 +532,19 @@ void *modes_host_alloc(size_t nbytes) {
 
 void modes_host_free(void *p) { if (p) cudaFreeHost(p); }
 
-int modes_get_kernel_times(const modes_ctx *ctx, float ms[4]) {
+int modes_get_kernel_times(modes_ctx *ctx, float ms[4]) {
     if (!ctx || !ms) return -1;
-    memcpy(ms, ctx->times, sizeof(ctx->times));
+    ms[0] = ms[1] = ms[2] = ms[3] = 0.f;
+    if (!ctx->prof_ready) return 0;
+    double a = 0, b = 0, c = 0; int n = 0;
+    for (; ctx->prof_tail < ctx->prof_head; ctx->prof_tail++) {
+        cudaEvent_t *pe = ctx->prof_ev[ctx->prof_tail % modes_ctx::kProfRing];
+        if (cudaEventSynchronize(pe[2]) != cudaSuccess) continue;
+        float x = 0, y = 0, z = 0;
+        cudaEventElapsedTime(&x, pe[0], pe[1]); cudaEventElapsedTime(&y, pe[1], pe[2]); cudaEventElapsedTime(&z, pe[0], pe[2]);
+        a += x; b += y; c += z; n++;
+    }
+    if (n) { ms[0] = (float)(a / n); ms[1] = (float)(b / n); ms[2] = (float)(c / n); ms[3] = (float)n; }
     return 0;
 }
 

@@ -365,16 +365,14 @@ __device__ __forceinline__ bool unconditionally_good(const PassResult &R) {
     return (R.flags & MODES_EVAL_DECODED) && R.crc == 0 && (R.msgtype == 11 || R.msgtype == 17 || R.msgtype == 18);
 }
 
-// Word k (0..5) of a modes_frame_eval as laid out in memory.
-__device__ __forceinline__ uint32_t eval_word(const PassResult &R, int k) {
-    switch (k) {
-        case 0: return __byte_perm(R.W[0], 0, 0x0123);
-        case 1: return __byte_perm(R.W[1], 0, 0x0123);
-        case 2: return __byte_perm(R.W[2], 0, 0x0123);
-        case 3: return (R.W[3] >> 24) | ((R.W[3] >> 8) & 0xff00u) | (R.msgtype << 16) | (R.flags << 24);
-        case 4: return R.errorbit | (R.nfixed << 8);
-        default: return R.crc;
-    }
+// The six 32-bit words of a modes_frame_eval as laid out in memory.
+__device__ __forceinline__ void eval_words(const PassResult &R, uint32_t w[6]) {
+    w[0] = __byte_perm(R.W[0], 0, 0x0123);
+    w[1] = __byte_perm(R.W[1], 0, 0x0123);
+    w[2] = __byte_perm(R.W[2], 0, 0x0123);
+    w[3] = (R.W[3] >> 24) | ((R.W[3] >> 8) & 0xff00u) | ((R.msgtype & 0xffu) << 16) | ((R.flags & 0xffu) << 24);
+    w[4] = (R.errorbit & 0xffu) | ((R.nfixed & 0xffu) << 8);
+    w[5] = R.crc & 0xffffffu;
 }
 
 constexpr int kEvalThreads = 256;
@@ -499,11 +497,13 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
         }
 
         // one coalesced 56-byte record: lanes 0..13 write one word each
-        uint32_t word;
-        if (lane == 0) word = (uint32_t)t;
-        else if (lane == 1) word = (uint32_t)(t >> 32);
-        else if (lane < 8) word = eval_word(P1, lane - 2);
-        else word = eval_word(P2, lane - 8);
+        uint32_t rec[14];
+        rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
+        eval_words(P1, rec + 2);
+        eval_words(P2, rec + 8);
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 14; k++) word = (lane == k) ? rec[k] : word;
         if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = word;
     }
 }
@@ -564,7 +564,11 @@ eval_frames_kernel(const uint8_t *__restrict__ frames, modes_frame_eval *out, ui
         R.flags = MODES_EVAL_GATE_OK | MODES_EVAL_DECODED;
         crc_and_fix(F, msgbits, R.msgtype, fix_errors, aggressive, s_syn, s_hash, lane, R.crc, R.errorbit, R.nfixed);
         frame_words(F, R.W);
-        if (lane < 6) reinterpret_cast<uint32_t *>(out + f)[lane] = eval_word(R, lane);
+        uint32_t rec[6], word = 0;
+        eval_words(R, rec);
+#pragma unroll
+        for (int k = 0; k < 6; k++) word = (lane == k) ? rec[k] : word;
+        if (lane < 6) reinterpret_cast<uint32_t *>(out + f)[lane] = word;
     }
 }
 

@@ -1,0 +1,78 @@
+"""Multi-GPU decode: contiguous runs of whole reference buffers per rank.
+
+The sample path shards with no data-path collective: a
+candidate's evaluation depends only on samples [s-1, s+239] and on its index
+inside its 131072-sample reference buffer, so rank r scans buffers
+[r*B, (r+1)*B) given the 476 stream bytes that precede them.  The only
+exchange is the gather of candidate records (56 bytes each) and tile tables to
+rank 0, which replays the order-dependent half (retry/skip state machine, ICAO
+cache — dump1090.c:1769-1791, :898-983) over the shards in stream order.
+
+One process per GPU; torch.distributed supplies the gather (NCCL on GPUs; the
+same code runs over gloo with CPU tensors for the host-logic tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def shard_plan(total_buffers: int, world: int):
+    """Contiguous, near-equal runs of whole buffers: [(first, count)] per rank."""
+    base, extra = divmod(total_buffers, world)
+    plan, first = [], 0
+    for r in range(world):
+        n = base + (1 if r < extra else 0)
+        plan.append((first, n))
+        first += n
+    return plan
+
+
+def carry_before(stream: np.ndarray, first_buffer: int):
+    """The 476 stream bytes preceding buffer `first_buffer` (None at stream start)."""
+    if first_buffer == 0:
+        return None
+    off = first_buffer * api.BUFFER_BYTES
+    return bytes(stream[off - api.CARRY_BYTES: off])
+
+
+def gather_records(cands, tiles, n_cand: int, dist=None, group=None, dst: int = 0):
+    """Gather per-rank (candidate records, tile table) to rank `dst`.
+
+    cands: uint8 tensor holding >= n_cand*56 bytes (device tensor under NCCL, CPU
+    tensor under gloo); tiles: uint8 tensor of the rank's tile table.  Returns on
+    dst a list of (cands_bytes_tensor[:n*56], tiles_tensor) per rank, else None.
+    Sizes are exchanged first so only max(n) records per rank travel.
+    """
+    import torch
+    if dist is None or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return [(cands[: n_cand * 56], tiles)]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    meta = torch.tensor([n_cand, tiles.numel()], dtype=torch.int64, device=cands.device)
+    metas = [torch.zeros_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    metas = [m.tolist() for m in metas]
+    max_c = max(m[0] for m in metas) * 56
+    max_t = max(m[1] for m in metas)
+    send_c = cands[:max_c] if cands.numel() >= max_c else torch.cat(
+        [cands, torch.zeros(max_c - cands.numel(), dtype=torch.uint8, device=cands.device)])
+    send_t = tiles[:max_t] if tiles.numel() >= max_t else torch.cat(
+        [tiles, torch.zeros(max_t - tiles.numel(), dtype=torch.uint8, device=tiles.device)])
+    if rank == dst:
+        rc = [torch.empty(max_c, dtype=torch.uint8, device=cands.device) for _ in range(world)]
+        rt = [torch.empty(max_t, dtype=torch.uint8, device=tiles.device) for _ in range(world)]
+        dist.gather(send_c.contiguous(), rc, dst=dst, group=group)
+        dist.gather(send_t.contiguous(), rt, dst=dst, group=group)
+        return [(rc[r][: metas[r][0] * 56], rt[r][: metas[r][1]]) for r in range(world)]
+    dist.gather(send_c.contiguous(), None, dst=dst, group=group)
+    dist.gather(send_t.contiguous(), None, dst=dst, group=group)
+    return None
+
+
+def resolve_gathered(resolver, gathered, plan) -> None:
+    """Rank 0: replay the sequential half over the shards in stream order."""
+    for (c, t), (first, _n) in zip(gathered, plan):
+        c_np = np.frombuffer(c.cpu().numpy().tobytes(), dtype=api.CANDIDATE_DTYPE)
+        t_np = np.frombuffer(t.cpu().numpy().tobytes(), dtype=api.TILE_DTYPE)
+        resolver.run(c_np, t_np, buffer_base=first)

@@ -125,6 +125,11 @@ void        modes_destroy(modes_ctx *ctx);
 const char *modes_last_error(const modes_ctx *ctx);                  /* ctx may be NULL: create() error */
 int         modes_set_sink(modes_ctx *ctx, modes_sink_fn fn, void *user);
 
+/* Alternative to a callback: append every delivered message to a caller-owned
+ * array (NULL/0 to stop).  modes_output_count() keeps counting past capacity. */
+int    modes_set_output(modes_ctx *ctx, modes_message *out, size_t capacity);
+size_t modes_output_count(const modes_ctx *ctx);
+
 /* ---- streaming decode: the main loop, dump1090.c:2968-2990 -------------- */
 /* Feed the next `nbytes` of the u8 I/Q stream (host memory, pinned or not).
  * Whole reference buffers are decoded as they complete.  0 = ok, <0 = error. */
@@ -178,12 +183,14 @@ int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
 int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out);
 
 /* ---- plumbing ----------------------------------------------------------- */
-void *modes_stream(modes_ctx *ctx);                    /* the context's cudaStream_t */
+void *modes_stream(modes_ctx *ctx);                    /* the cudaStream_t modes_detect_device launches on */
+int   modes_set_stream(modes_ctx *ctx, void *cuda_stream);   /* use the caller's stream for it (NULL: own) */
 void *modes_host_alloc(size_t nbytes);                 /* pinned host memory for modes_process input */
 void  modes_host_free(void *p);
-/* ms of the last batch per kernel when cfg.profile: [0] scan (magnitude+preamble),
- * [1] frame evaluation, [2] whole device batch, [3] launches in the batch. */
-int  modes_get_kernel_times(const modes_ctx *ctx, float ms[4]);
+/* cfg.profile: mean device time (CUDA events on the launching stream) per batch
+ * since the previous call: [0] scan kernel (magnitude+preamble), [1] frame
+ * evaluation kernel, [2] both, [3] number of batches averaged. */
+int  modes_get_kernel_times(modes_ctx *ctx, float ms[4]);
 /* Cumulative count of kernel launches issued by this context. */
 uint64_t modes_launch_count(const modes_ctx *ctx);
 

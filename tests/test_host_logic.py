@@ -1,0 +1,103 @@
+"""CPU (-m "not gpu"): the product's host-side code and the C-ABI surface (no device compute)."""
+import ctypes
+import hashlib
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import checker as C
+import golden_util as G
+from dump1090_b200 import api, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    header = (ROOT / "include" / "modes_b200.h").read_text()
+    declared = set(re.findall(r"\b(modes_[a-z_0-9]+)\s*\(", header)) - {"modes_sink_fn"}
+    assert declared == set(api.EXPORTS)
+    L = ctypes.CDLL(str(api.LIB_PATH))
+    for name in sorted(declared):
+        assert hasattr(L, name), name
+    assert L.modes_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert ctypes.sizeof(api.Message) == ctypes.sizeof(C.Msg) == 200
+    assert ctypes.sizeof(api.FrameEval) == ctypes.sizeof(C.Pass) == 24
+    assert ctypes.sizeof(api.Candidate) == ctypes.sizeof(C.Cand) == 56
+    assert api.CANDIDATE_DTYPE.itemsize == 56 and api.TILE_DTYPE.itemsize == 8
+    cfg = api.make_config()
+    assert (cfg.fix_errors, cfg.aggressive, cfg.check_crc, cfg.drop_eof_buffer) == (1, 0, 1, 0)   # dump1090.c:305-315
+
+
+def test_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        api.Decoder()
+
+
+def _resolve_with_product(data, kw):
+    cands = C.oracle_scan_candidates(data, fix=kw.get("fix", 1), aggressive=kw.get("aggressive", 0),
+                                     drop_eof=kw.get("drop_eof", 0))
+    arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE) if cands \
+        else np.zeros(0, dtype=api.CANDIDATE_DTYPE)
+    # split the candidate list into a few "tiles" to exercise the tile walk
+    cuts = sorted({0, len(cands) // 3, len(cands) // 2, len(cands)})
+    tiles = np.array([(a, b - a) for a, b in zip(cuts, cuts[1:])] or [(0, 0)], dtype=api.TILE_DTYPE)
+    r = api.Resolver(fix_errors=kw.get("fix", 1), aggressive=kw.get("aggressive", 0), check_crc=kw.get("check_crc", 1))
+    r.run(arr, tiles)
+    return r.take_messages(), list(r.stats().values())
+
+
+@pytest.mark.parametrize("name,cid", G.CASES)
+def test_resolver_reproduces_golden(name, cid, checker_libs):
+    """Product resolve + field decode (modes_resolve.cpp), fed with the oracle's candidate records,
+    must reproduce the reference's messages, fields and statistics."""
+    doc = G.load(name)
+    case = doc["cases"][cid]
+    msgs, st = _resolve_with_product(G.make_input(doc), case["flags"])
+    assert [C.msg_fields(m) for m in msgs] == case["messages"]
+    assert st == case["stats"]
+
+
+def test_resolver_sample_positions(checker_libs):
+    data = synth.random_traffic(300000, 300, 21)
+    msgs, _ = _resolve_with_product(data, {})
+    exp, _ = C.oracle_decode(data)
+    assert [m.sample_pos for m in msgs] == [m.sample_pos for m in exp]
+
+
+def test_resolver_shard_boundaries_are_invisible(checker_libs):
+    """Feeding the resolver buffer by buffer (as shards arrive from different GPUs) changes nothing."""
+    data = synth.random_traffic(600000, 700, 22)
+    cands = C.oracle_scan_candidates(data)
+    arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE)
+    whole = api.Resolver()
+    whole.run(arr, np.array([(0, arr.size)], dtype=api.TILE_DTYPE))
+    ref = [m.raw_line() for m in whole.take_messages()]
+    parts = api.Resolver()
+    for k in range(int(arr["t"].max() >> 17) + 1):
+        sel = arr[(arr["t"] >> 17) == k].copy()
+        sel["t"] -= k << 17                       # shard-local positions + buffer_base
+        parts.run(sel, np.array([(0, sel.size)], dtype=api.TILE_DTYPE), buffer_base=k)
+    assert [m.raw_line() for m in parts.take_messages()] == ref
+    assert parts.stats() == whole.stats()
+
+
+def test_synth_is_deterministic():
+    s = synth.random_traffic(50000, 60, 3)
+    assert hashlib.sha256(s.tobytes()).hexdigest() == hashlib.sha256(synth.random_traffic(50000, 60, 3).tobytes()).hexdigest()
+    assert s.dtype == np.uint8 and s.size == 100000
+    t = synth.tile_to(s, 250001)
+    assert t.size == 250001 and np.array_equal(t[:100000], s) and np.array_equal(t[100000:200000], s)
+
+
+def test_synth_parity_against_known_frames():
+    for hx in ("8D451E8B99019699C00B0A81F36E", "8D4B969699155600E87406F5B69F"):
+        b = bytes.fromhex(hx)
+        assert synth.make_frame(17, b[0] & 7, b[1:11]) == b
