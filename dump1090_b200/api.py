@@ -94,7 +94,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_stats", "modes_decode_frame", "modes_stream", "modes_set_stream",
+           "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_host_alloc",
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
 
@@ -128,6 +128,9 @@ def lib():
         L.modes_resolver_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, SINK_FN,
                                          C.c_void_p]
         L.modes_resolver_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        L.modes_resolver_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_resolver_output_count.restype = C.c_size_t
+        L.modes_resolver_output_count.argtypes = [C.c_void_p]
         L.modes_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Message)]
         L.modes_stream.restype = C.c_void_p
         L.modes_stream.argtypes = [C.c_void_p]
@@ -354,14 +357,27 @@ class Resolver:
     def run(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0) -> None:
         cands = np.ascontiguousarray(cands)
         tiles = np.ascontiguousarray(tiles)
-        rc = lib().modes_resolver_run(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base,
-                                      self._collector.fn, None)
+        fn = C.cast(None, SINK_FN) if getattr(self, "_native", False) else self._collector.fn
+        rc = lib().modes_resolver_run(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base, fn, None)
         if rc:
             raise RuntimeError("modes_resolver_run failed")
 
     def take_messages(self):
         out, self._collector.messages = self._collector.messages, []
         return out
+
+    def set_output_array(self, capacity: int):
+        """Fill a preallocated array in place instead of calling back into Python per message."""
+        self._out = (Message * capacity)() if capacity > 0 else None
+        self._native = capacity > 0
+        lib().modes_resolver_set_output(self._h, self._out, max(capacity, 0))
+        return self._out
+
+    def rearm_output(self) -> None:
+        lib().modes_resolver_set_output(self._h, self._out, len(self._out))
+
+    def output_count(self) -> int:
+        return int(lib().modes_resolver_output_count(self._h))
 
     def stats(self) -> dict:
         st = Stats()

@@ -61,12 +61,7 @@ struct modes_ctx {
     int64_t buffers_done = 0;
     bool finished = false;
     ResolveState rs;
-    modes_sink_fn sink = nullptr;
-    void *sink_user = nullptr;
-    modes_sink_fn user_sink = nullptr;    // what the caller registered
-    void *user_sink_user = nullptr;
-    modes_message *out_buf = nullptr;     // modes_set_output
-    size_t out_cap = 0, out_n = 0;
+    MessageOut out;                       // modes_set_sink / modes_set_output
     cudaStream_t own_detect_stream = nullptr;
     std::string err;
     uint64_t launches = 0;
@@ -228,7 +223,7 @@ int collect(modes_ctx *ctx, Slot &s) {
     CK(ctx, cudaMemcpyAsync(s.h_tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaStreamSynchronize(s.stream));
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
-    resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->sink, ctx->sink_user);
+    resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->out);
     return 0;
 }
 
@@ -329,35 +324,21 @@ modes_ctx *modes_create(const modes_config *cfg) {
     return ctx;
 }
 
-static void tee_sink(void *user, const modes_message *mm) {
-    modes_ctx *ctx = static_cast<modes_ctx *>(user);
-    if (ctx->out_buf && ctx->out_n < ctx->out_cap) ctx->out_buf[ctx->out_n] = *mm;
-    ctx->out_n++;
-    if (ctx->user_sink) ctx->user_sink(ctx->user_sink_user, mm);
-}
-
-static void rewire_sink(modes_ctx *ctx) {
-    if (ctx->out_buf) { ctx->sink = tee_sink; ctx->sink_user = ctx; }
-    else { ctx->sink = ctx->user_sink; ctx->sink_user = ctx->user_sink_user; }
-}
-
 int modes_set_sink(modes_ctx *ctx, modes_sink_fn fn, void *user) {
     if (!ctx) return -1;
-    ctx->user_sink = fn; ctx->user_sink_user = user;
-    rewire_sink(ctx);
+    ctx->out.sink = fn; ctx->out.user = user;
     return 0;
 }
 
 int modes_set_output(modes_ctx *ctx, modes_message *out, size_t capacity) {
     if (!ctx) return -1;
-    ctx->out_buf = capacity ? out : nullptr;
-    ctx->out_cap = out ? capacity : 0;
-    ctx->out_n = 0;
-    rewire_sink(ctx);
+    ctx->out.array = capacity ? out : nullptr;
+    ctx->out.capacity = out ? capacity : 0;
+    ctx->out.count = 0;
     return 0;
 }
 
-size_t modes_output_count(const modes_ctx *ctx) { return ctx ? ctx->out_n : 0; }
+size_t modes_output_count(const modes_ctx *ctx) { return ctx ? ctx->out.count : 0; }
 
 int modes_set_stream(modes_ctx *ctx, void *cuda_stream) {
     if (!ctx) return -1;
@@ -472,11 +453,11 @@ int modes_resolve(modes_ctx *ctx, const modes_candidate *candidates, const modes
                   int64_t buffer_base) {
     if (!ctx || !tiles) return -1;
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
-    resolve_candidates(ctx->rs, rc, candidates, tiles, n_tiles, buffer_base, ctx->sink, ctx->sink_user);
+    resolve_candidates(ctx->rs, rc, candidates, tiles, n_tiles, buffer_base, ctx->out);
     return 0;
 }
 
-struct modes_resolver { ResolveState rs; ResolveConfig rc; };
+struct modes_resolver { ResolveState rs; ResolveConfig rc; MessageOut out; };
 
 modes_resolver *modes_resolver_create(const modes_config *cfg) {
     modes_resolver *r = new (std::nothrow) modes_resolver();
@@ -493,9 +474,20 @@ void modes_resolver_destroy(modes_resolver *r) { delete r; }
 int modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
                        size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user) {
     if (!r || !tiles) return -1;
-    resolve_candidates(r->rs, r->rc, candidates, tiles, n_tiles, buffer_base, sink, user);
+    r->out.sink = sink; r->out.user = user;
+    resolve_candidates(r->rs, r->rc, candidates, tiles, n_tiles, buffer_base, r->out);
     return 0;
 }
+
+int modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity) {
+    if (!r) return -1;
+    r->out.array = capacity ? out : nullptr;
+    r->out.capacity = out ? capacity : 0;
+    r->out.count = 0;
+    return 0;
+}
+
+size_t modes_resolver_output_count(const modes_resolver *r) { return r ? r->out.count : 0; }
 
 int modes_resolver_stats(const modes_resolver *r, modes_stats *out) {
     if (!r || !out) return -1;

@@ -78,9 +78,15 @@ struct ResolveState {
 
 struct ResolveConfig { int fix_errors, aggressive, check_crc; };
 
+// Where delivered messages go: a callback, and/or a caller-owned array that is
+// filled in place (count keeps running past capacity).
+struct MessageOut {
+    modes_sink_fn sink = nullptr; void *user = nullptr;
+    modes_message *array = nullptr; size_t capacity = 0; size_t count = 0;
+};
+
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
-                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base,
-                        modes_sink_fn sink, void *user);
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out);
 // The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
 int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
 

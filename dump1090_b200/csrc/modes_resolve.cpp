@@ -12,8 +12,17 @@
 //   * statistics (dump1090.c:1651, :1662, :1738-1753, :1122-1126)
 //   * the sink gate (dump1090.c:1803) and struct modesMessage field decode
 //     (:1133-1179, :1212-1308) for delivered messages
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
 #include "modes_internal.h"
 
 namespace modes {
@@ -124,7 +133,34 @@ static void decode_fields(modes_message *o) {
     }
 }
 
-int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *o) {
+// Order-dependent verdict of decodeModesMessage for one evaluated frame
+// (dump1090.c:1108-1128 statistics, :1183-1210 ICAO logic) without building the
+// message: returns crcok; *iid and *ap_addr receive the DF11 interrogator id and
+// the recovered address of an address/parity format (0 when not applicable).
+static inline int judge(ResolveState &st, const modes_frame_eval &p, uint32_t *iid, uint32_t *ap_addr) {
+    *iid = 0; *ap_addr = 0;
+    if (p.nfixed == 1) st.stats[6]++;                      // dump1090.c:1122-1126
+    else if (p.nfixed == 2) st.stats[7]++;
+    const int df = p.msgtype;
+    int crcok = p.crc == 0;
+    if (df == 11 || df == 17 || df == 18) {
+        const uint32_t addr = ((uint32_t)p.msg[1] << 16) | ((uint32_t)p.msg[2] << 8) | (uint32_t)p.msg[3];
+        if (crcok && p.nfixed == 0) st.icao[icao_slot(addr)] = addr;          // :1198-1200
+        if (df == 11 && !crcok && p.crc < 80 && icao_seen(st, addr)) {         // :1204-1209
+            *iid = p.crc;
+            crcok = 1;
+        }
+        return crcok;
+    }
+    // parity field = CRC ^ address, so the syndrome is the sender's address (:962-974)
+    if ((df == 0 || df == 4 || df == 5 || df == 16 || df == 20 || df == 21 || df == 24) && icao_seen(st, p.crc)) {
+        *ap_addr = p.crc;
+        return 1;
+    }
+    return 0;
+}
+
+static void build_message(const modes_frame_eval &p, int crcok, uint32_t iid, uint32_t ap_addr, modes_message *o) {
     std::memset(o, 0, sizeof(*o));
     std::memcpy(o->msg, p.msg, 14);
     o->msgtype = p.msgtype;
@@ -132,53 +168,106 @@ int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *o
     o->crc = p.crc;
     o->nfixed = p.nfixed;
     o->errorbit = p.nfixed ? (int)p.errorbit : -1;
-    o->crcok = p.crc == 0;
-    if (p.nfixed == 1) st.stats[6]++;                      // dump1090.c:1122-1126
-    else if (p.nfixed == 2) st.stats[7]++;
+    o->crcok = crcok;
+    o->iid = (int32_t)iid;
     decode_fields(o);
-    const int df = o->msgtype;
-    if (df == 11 || df == 17 || df == 18) {
-        const uint32_t addr = ((uint32_t)o->aa1 << 16) | ((uint32_t)o->aa2 << 8) | (uint32_t)o->aa3;
-        if (o->crcok && o->errorbit == -1) st.icao[icao_slot(addr)] = addr;
-        if (df == 11 && !o->crcok && o->crc < 80 && icao_seen(st, addr)) {
-            o->iid = (int32_t)o->crc;
-            o->crcok = 1;
-        }
-    } else {
-        o->crcok = 0;
-        if (df == 0 || df == 4 || df == 5 || df == 16 || df == 20 || df == 21 || df == 24) {
-            // parity field = CRC ^ address, so the syndrome is the sender's address
-            const uint32_t addr = p.crc;
-            if (icao_seen(st, addr)) {
-                o->aa1 = (addr >> 16) & 0xff; o->aa2 = (addr >> 8) & 0xff; o->aa3 = addr & 0xff;
-                o->crcok = 1;
-            }
+    if (ap_addr) { o->aa1 = (ap_addr >> 16) & 0xff; o->aa2 = (ap_addr >> 8) & 0xff; o->aa3 = ap_addr & 0xff; }
+}
+
+int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *o) {
+    uint32_t iid, ap;
+    const int crcok = judge(st, p, &iid, &ap);
+    build_message(p, crcok, iid, ap, o);
+    return crcok;
+}
+
+// ---- delivered messages: verdicts first (sequential), structs second (parallel)
+
+// What the sequential pass decides about one delivered message; the 200-byte
+// struct is built from it afterwards, in parallel for array output.
+struct Delivery {
+    const modes_frame_eval *eval;
+    int64_t sample_pos;
+    uint32_t iid, ap_addr;
+    uint8_t crcok, phase_corrected;
+};
+
+static inline void materialise(const Delivery &d, modes_message *mm) {
+    build_message(*d.eval, d.crcok, d.iid, d.ap_addr, mm);
+    mm->sample_pos = d.sample_pos;
+    mm->phase_corrected = d.phase_corrected;
+}
+
+// A few helper threads for building message structs; created on first use.
+class BuildPool {
+  public:
+    static BuildPool &get() { static BuildPool *p = new BuildPool();  /* never destroyed: workers are detached */ return *p; }
+    void run(size_t n, const std::function<void(size_t, size_t)> &fn) {
+        if (workers_.empty() || n < 2048) { fn(0, n); return; }
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &fn; n_ = n; next_ = 0; pending_ = workers_.size(); gen_++;
+        cv_.notify_all();
+        lk.unlock();
+        work();                                            // the caller helps
+        lk.lock();
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+  private:
+    BuildPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        unsigned nw = hw > 16 ? 7 : (hw > 2 ? hw / 2 - 1 : 0);
+        for (unsigned i = 0; i < nw; i++) workers_.emplace_back([this] { loop(); });
+        for (auto &t : workers_) t.detach();
+    }
+    void work() {
+        for (;;) {
+            size_t b = next_.fetch_add(1024);
+            if (b >= n_) break;
+            (*fn_)(b, b + 1024 < n_ ? b + 1024 : n_);
         }
     }
-    return o->crcok;
-}
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            lk.unlock();
+            work();
+            lk.lock();
+            if (--pending_ == 0) done_.notify_all();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t, size_t)> *fn_ = nullptr;
+    size_t n_ = 0, pending_ = 0;
+    std::atomic<size_t> next_{0};
+    uint64_t gen_ = 0;
+};
 
 // One evaluated attempt, as detectModeS handles it after the delta gate.
 // Returns true when the message is good (the scan skips past it).
 static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const modes_frame_eval &p, bool retry,
-                           int64_t sample_pos, modes_sink_fn sink, void *user) {
+                           int64_t sample_pos, std::vector<Delivery> &deliveries) {
     if (!(p.flags & MODES_EVAL_DECODED)) return false;
-    modes_message mm;
-    const int crcok = finish_message(st, p, &mm);
+    uint32_t iid, ap;
+    const int crcok = judge(st, p, &iid, &ap);
     if (crcok || retry) {                                  // dump1090.c:1738-1753
         if (!(p.flags & MODES_EVAL_ERRORS)) st.stats[2]++;
-        if (mm.errorbit == -1) st.stats[crcok ? 3 : 4]++;
+        if (p.nfixed == 0) st.stats[crcok ? 3 : 4]++;
         else { st.stats[4]++; st.stats[5]++; st.stats[6]++; }
     }
-    mm.sample_pos = sample_pos;
-    if (crcok && retry) mm.phase_corrected = 1;            // dump1090.c:1772-1773
-    if (sink && (cfg.check_crc == 0 || crcok)) sink(user, &mm);
+    if (cfg.check_crc == 0 || crcok)                       // dump1090.c:1803; :1772-1773
+        deliveries.push_back(Delivery{&p, sample_pos, iid, ap, (uint8_t)crcok, (uint8_t)(crcok && retry)});
     return crcok != 0;
 }
 
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
-                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base,
-                        modes_sink_fn sink, void *user) {
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out) {
+    static thread_local std::vector<Delivery> deliveries;
+    deliveries.clear();
     for (size_t ti = 0; ti < n_tiles; ti++) {
         const modes_candidate *c = cands + tiles[ti].offset;
         for (uint32_t k = 0; k < tiles[ti].count; k++, c++) {
@@ -191,14 +280,36 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
             if (!(p1.flags & MODES_EVAL_GATE_OK)) continue;        // dump1090.c:1723-1726
             const int64_t pos = buffer * (int64_t)kBufSamples + j - MODES_CARRY_SAMPLES;
             const uint32_t skip = (uint32_t)(8 + bits_by_type(p1.msgtype)) * 2 + 1;
-            if (attempt(st, cfg, p1, false, pos, sink, user)) { st.next_j = j + skip; continue; }
+            if (attempt(st, cfg, p1, false, pos, deliveries)) { st.next_j = j + skip; continue; }
             if (j) st.stats[1]++;                          // dump1090.c:1660-1663
             const modes_frame_eval &p2 = c->pass[1];
             if (!(p2.flags & MODES_EVAL_GATE_OK)) continue;
             const uint32_t skip2 = (uint32_t)(8 + bits_by_type(p2.msgtype)) * 2 + 1;
-            if (attempt(st, cfg, p2, true, pos, sink, user)) st.next_j = j + skip2;
+            if (attempt(st, cfg, p2, true, pos, deliveries)) st.next_j = j + skip2;
         }
     }
+    static const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
+    timespec ta, tb; if (dbg) clock_gettime(CLOCK_MONOTONIC, &ta);
+    // Build the delivered structs: in place and in parallel for array output, then the
+    // callback (if any) sequentially in stream order.
+    const size_t n = deliveries.size();
+    size_t in_array = 0;
+    if (out.array && out.count < out.capacity) {
+        in_array = out.capacity - out.count < n ? out.capacity - out.count : n;
+        modes_message *base = out.array + out.count;
+        const Delivery *d = deliveries.data();
+        BuildPool::get().run(in_array, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) materialise(d[i], base + i); });
+    }
+    if (out.sink) {
+        for (size_t i = 0; i < n; i++) {
+            if (i < in_array) { out.sink(out.user, out.array + out.count + i); continue; }
+            modes_message tmp;
+            materialise(deliveries[i], &tmp);
+            out.sink(out.user, &tmp);
+        }
+    }
+    out.count += n;
+    if (dbg) { clock_gettime(CLOCK_MONOTONIC, &tb); fprintf(stderr, "[resolve] %zu deliveries built in %.3f ms\n", n, (tb.tv_sec-ta.tv_sec)*1e3+(tb.tv_nsec-ta.tv_nsec)*1e-6); }
 }
 
 }  // namespace modes

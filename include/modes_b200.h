@@ -176,6 +176,8 @@ void modes_resolver_destroy(modes_resolver *r);
 int  modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
                         size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user);
 int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
+int    modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity);   /* like modes_set_output */
+size_t modes_resolver_output_count(const modes_resolver *r);
 
 /* decodeModesMessage() on frame bytes (the reference's hex door,
  * decodeHexMessage dump1090.c:2472-2502): CRC, fix and field decode run on the
