@@ -71,107 +71,219 @@ __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
 }
 
 // ------------------------------------------------------------------ K1: scan
+//
+// "Strip scan".  One warp owns one tile of 4096 positions at a time; lane l walks
+// the 128 consecutive positions [128l, 128l+128) of the tile with a rolling
+// register window, so every sample's squared magnitude and every derived
+// quantity is computed exactly once (plus a 17-sample overlap per strip).
+//
+// Data movement: the tile's raw I/Q (8 KB + 48 B lookahead) is copied
+// global -> shared with cp.async (16 B per lane per instruction, fully
+// coalesced, no register staging), two stages per warp so the next tile streams
+// in while this one is scanned.  In shared memory each 256-byte strip is padded
+// to 272 bytes, which makes the per-lane 16-byte reads of a warp conflict-free.
+//
+// Arithmetic: squared magnitudes n = i*i+q*q are held two per 32-bit register as
+// 15-bit fields (n clamped to 32767, order preserving on the reachable values),
+// so one 32-bit instruction works on two positions:
+//     cX      = 0x7fff7fff - X          (complement, per half)
+//     L + cR  has bit 15 / bit 31 set   <=>  L > R   in the low / high half
+// The ten comparisons of dump1090.c:1602-1611 for position j reduce to
+//     min(m0,m2) > max(m1,m3)      m0 > max(m4,m5,m6)
+//     m9 > max(m6,m8)              m7 > m8
+// i.e. per pair of positions: 3 packed min, 1 packed min3, 4 adds, 2 ANDs.
+// Survivors (~1% of positions) then get the exact "high" tests
+// (dump1090.c:1624-1642) on magnitudes from the table, balanced across the warp.
 
-constexpr int kScanThreads = 256;      // 8 samples per thread = one 2048-sample tile per pass
+constexpr int kStripSamples = 128;                       // per lane per tile
+constexpr int kStripPitch16 = 17;                        // 272-byte pitch in 16-byte units
+constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
+constexpr int kStageBytes = (32 * kStripPitch16 + 3) * 16;   // 8752: 32 strips + 3 lookahead chunks
+constexpr int kSurvivorCap = 512;
+constexpr int kScanWarpSmem = 2 * kStageBytes + 128 * 4 + kSurvivorCap * 2;
+constexpr uint32_t kK15 = 0x7fff7fffu;
+static_assert(kTileSamples == 32 * kStripSamples, "tile = 32 strips");
 
-// Exact version of the tests of dump1090.c:1624-1642 for a position that already
-// passed the ten comparisons; ns = squared magnitudes of the tile (+16 lookahead).
-__device__ __forceinline__ bool high_tests(const uint16_t *ns, int pos, const uint16_t *__restrict__ lutn) {
-    int m0 = __ldg(lutn + ns[pos]),      m2 = __ldg(lutn + ns[pos + 2]);
-    int m7 = __ldg(lutn + ns[pos + 7]),  m9 = __ldg(lutn + ns[pos + 9]);
-    int m4 = __ldg(lutn + ns[pos + 4]),  m5 = __ldg(lutn + ns[pos + 5]);
-    int m11 = __ldg(lutn + ns[pos + 11]), m12 = __ldg(lutn + ns[pos + 12]);
-    int m13 = __ldg(lutn + ns[pos + 13]), m14 = __ldg(lutn + ns[pos + 14]);
-    int high = (m0 + m2 + m7 + m9) / 6;
-    return m4 < high && m5 < high && m11 < high && m12 < high && m13 < high && m14 < high;
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
 
-__global__ void __launch_bounds__(kScanThreads)
+// Two I/Q pairs -> two clamped squared magnitudes, packed (low half = first sample).
+__device__ __forceinline__ uint32_t n2_pack15(uint32_t raw) {
+    uint32_t a = __vabsdiffu4(raw, 0x7f7f7f7fu);
+    uint32_t n0 = __dp4a(a & 0xffffu, a, 0u);
+    uint32_t nt = __dp4a(a, a, 0u);
+    return __vminu2(n0 + ((nt - n0) << 16), kK15);
+}
+
+// Queue the copy of tile g (raw I/Q of virtual chunks [512g, 512g+515)) into a stage.
+__device__ __forceinline__ void stage_tile(const BatchView &in, uint32_t stage_addr, uint32_t g, uint64_t n_vchunks,
+                                           int lane) {
+    const uint64_t c0 = (uint64_t)g * kTileChunks;
+    if (c0 >= kHaloSamples / 8 && c0 + kTileChunks + 3 <= n_vchunks) {
+        // interior tile: one base pointer, constant strides (chunk x = 32i+lane -> strip 2i+(lane>>4), slot lane&15)
+        const uint8_t *src = in.body + 16 * (c0 - kHaloSamples / 8) + 16 * lane;
+        const uint32_t dst = stage_addr + ((lane >> 4) * kStripPitch16 + (lane & 15)) * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i++) cp_async16(dst + i * (2 * kStripPitch16 * 16), src + 512 * i, 16u);
+        if (lane < 3) cp_async16(stage_addr + (32 * kStripPitch16 + lane) * 16, src + 512 * 16, 16u);
+    } else {
+        // first tile (carry block) and last tile (end of the batch)
+        for (int i = 0; i < 17; i++) {
+            const int x = 32 * i + lane;                 // chunk index inside the tile, 0..514
+            if (x >= kTileChunks + 3) break;
+            const uint64_t c = c0 + x;
+            const uint8_t *src = (c < kHaloSamples / 8) ? in.halo + 16 * c : in.body + 16 * (c - kHaloSamples / 8);
+            const bool ok = c < n_vchunks;
+            cp_async16(stage_addr + ((x >> 4) * kStripPitch16 + (x & 15)) * 16, ok ? src : in.halo, ok ? 16u : 0u);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// Magnitude of sample s (tile-local, 0..4119) from the staged raw bytes.
+__device__ __forceinline__ int staged_mag(const uint8_t *stage, int s, const uint16_t *__restrict__ lutn) {
+    uint32_t w = *reinterpret_cast<const uint16_t *>(stage + (s >> 7) * (kStripPitch16 * 16) + (s & 127) * 2);
+    uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
+    return __ldg(lutn + __dp4a(a, a, 0u));
+}
+
+__global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
-    __shared__ uint4 s_n[2][kScanThreads + 2];      // u16 squared magnitudes, +16 lookahead
-    __shared__ uint32_t s_mask[2][kScanThreads / 4];
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *nat = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes);          // 4096 pass bits, natural order
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + 512);   // survivor positions
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint64_t n_vsamples = in.n_samples + kHaloSamples;
-    const uint64_t n_vchunks = n_vsamples / 8;
-    const uint64_t t_end = in.n_samples;            // valid t < N
+    const int lane = threadIdx.x;
+    const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
+    const uint64_t t_end = in.n_samples;
 
-    uint32_t tile = blockIdx.x;
-    uint4 raw = make_uint4(0, 0, 0, 0);
-    if (tile < n_tiles) raw = load_vchunk(in, (uint64_t)tile * kScanThreads + tid, n_vchunks);
+    uint32_t g = blockIdx.x;
+    if (g >= n_tiles) return;
+    stage_tile(in, smem_u32(smem), g, n_vchunks, lane);
 
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
-        const int buf = it & 1;
-        const uint64_t chunk0 = (uint64_t)tile * kScanThreads;
-        // prefetch the next tile's chunk while this one is processed
-        uint4 nxt = make_uint4(0, 0, 0, 0);
-        if (tile + gridDim.x < n_tiles)
-            nxt = load_vchunk(in, (uint64_t)(tile + gridDim.x) * kScanThreads + tid, n_vchunks);
-
-        s_n[buf][tid] = iq8_to_n8(raw);
-        if (tid < 2) s_n[buf][kScanThreads + tid] = iq8_to_n8(load_vchunk(in, chunk0 + kScanThreads + tid, n_vchunks));
-        __syncthreads();
-
-        // window of 24 squared magnitudes starting at this thread's first sample
-        uint4 a = s_n[buf][tid], b = s_n[buf][tid + 1], c = s_n[buf][tid + 2];
-        uint32_t x[24];
-        const uint32_t pk[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-        for (int k = 0; k < 12; k++) { x[2 * k] = pk[k] & 0xffffu; x[2 * k + 1] = pk[k] >> 16; }
-
-        // ten comparisons of dump1090.c:1602-1611, exact on squared magnitudes
-        uint32_t mask = 0;
-#pragma unroll
-        for (int p = 0; p < 8; p++) {
-            bool ok = x[p] > x[p + 1] && x[p + 1] < x[p + 2] && x[p + 2] > x[p + 3] && x[p + 3] < x[p] &&
-                      x[p + 4] < x[p] && x[p + 5] < x[p] && x[p + 6] < x[p] && x[p + 7] > x[p + 8] &&
-                      x[p + 8] < x[p + 9] && x[p + 9] > x[p + 6];
-            mask |= ok ? (1u << p) : 0u;
+    for (int it = 0; g < n_tiles; g += gridDim.x, ++it) {
+        const int cur = it & 1;
+        if (g + gridDim.x < n_tiles) {
+            stage_tile(in, smem_u32(smem) + (cur ^ 1) * kStageBytes, g + gridDim.x, n_vchunks, lane);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        // positions the reference never tests: t < 0, j >= 131070 (dump1090.c:1593), past the batch
-        if (mask) {
-            const uint64_t v0 = (chunk0 + tid) * 8;
+        __syncwarp();
+
+        // ---- scan this lane's strip: 16 chunks of 8 positions, rolling window of packed words
+        const uint8_t *st = smem + cur * kStageBytes;
+        const uint4 *sp = reinterpret_cast<const uint4 *>(st) + lane * kStripPitch16;
+        uint32_t P[76];
+        {
+            uint4 r0 = sp[0], r1 = sp[1];
+            P[0] = n2_pack15(r0.x); P[1] = n2_pack15(r0.y); P[2] = n2_pack15(r0.z); P[3] = n2_pack15(r0.w);
+            P[4] = n2_pack15(r1.x); P[5] = n2_pack15(r1.y); P[6] = n2_pack15(r1.z); P[7] = n2_pack15(r1.w);
+        }
+        uint32_t acc[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int p = 0; p < 8; p++) {
-                uint64_t v = v0 + p;
-                bool valid = v >= 2 && (v - 2) < t_end && (((uint32_t)(v - 2)) & (kBufSamples - 1)) < kScanLimit;
-                if (!valid) mask &= ~(1u << p);
+        for (int c = 0; c < 16; c++) {
+            {   // squared magnitudes of chunk c+2 (chunks 16,17 are the next strip's first two)
+                const int cc = c + 2;
+                uint4 r = sp[cc < 16 ? cc : cc + 1];
+                P[4 * cc + 0] = n2_pack15(r.x); P[4 * cc + 1] = n2_pack15(r.y);
+                P[4 * cc + 2] = n2_pack15(r.z); P[4 * cc + 3] = n2_pack15(r.w);
             }
-        }
-        reinterpret_cast<uint8_t *>(s_mask[buf])[tid] = (uint8_t)mask;
-        __syncthreads();
-
-        // One warp (rotating) finishes the tile: exact "high" tests on the few
-        // survivors, ordered compaction, one atomic per tile.
-        if (warp == (it & 7)) {
-            const uint16_t *ns = reinterpret_cast<const uint16_t *>(s_n[buf]);
-            uint32_t keep[2];
+            uint32_t T[4];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t w = s_mask[buf][2 * lane + h], k = 0;
-                for (uint32_t r = w; r; r &= r - 1) {
-                    int bit = __ffs(r) - 1;
-                    if (high_tests(ns, 64 * lane + 32 * h + bit, lutn)) k |= 1u << bit;
+            for (int u = 0; u < 4; u++) {
+                const int w = 4 * c + u;                 // packed word = positions 2w, 2w+1 of the strip
+                // odd-aligned pairs S[x] = (n[2x+1], n[2x+2]) and complements
+                const uint32_t S0 = __byte_perm(P[w], P[w + 1], 0x5432), S1 = __byte_perm(P[w + 1], P[w + 2], 0x5432);
+                const uint32_t S2 = __byte_perm(P[w + 2], P[w + 3], 0x5432);
+                const uint32_t S3 = __byte_perm(P[w + 3], P[w + 4], 0x5432), S4 = __byte_perm(P[w + 4], P[w + 5], 0x5432);
+                const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
+                const uint32_t cP2 = kK15 - P[w + 2], cP3 = kK15 - P[w + 3], cP4 = kK15 - P[w + 4];
+                const uint32_t A = __vminu2(P[w], P[w + 1]);                   // min(m0, m2)
+                const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
+                const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
+                const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
+                const uint32_t D1 = A + cB, D2 = P[w] + cW, D3 = S4 + cE, D4 = S3 + cP4;
+                T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2w / 2w+1 passes
+            }
+            // collect the 8 pass flags of this chunk (scrambled order, see decode below)
+            const int k = c & 3;
+            const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
+            acc[c >> 2] |= ((X >> (2 * k)) & (0x80808080u >> (2 * k))) | ((Y >> (2 * k + 1)) & (0x40404040u >> (2 * k)));
+        }
+
+        // ---- survivors -> compact list (tile order), dropping positions the reference never tests
+        nat[4 * lane + 0] = 0; nat[4 * lane + 1] = 0; nat[4 * lane + 2] = 0; nat[4 * lane + 3] = 0;
+        const uint32_t v_tile = g * (uint32_t)kTileSamples;
+        uint32_t cnt = __popc(acc[0]) + __popc(acc[1]) + __popc(acc[2]) + __popc(acc[3]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t round = 0; round < n_surv; round += kSurvivorCap) {
+            uint32_t idx = incl - cnt;                   // this lane's first slot in tile order
+#pragma unroll
+            for (int gq = 0; gq < 4; gq++) {
+                // ascending position order inside the word: chunk k, then position p
+                for (uint32_t r = acc[gq]; r;) {
+                    // lowest position first: scan chunks k=0..3 (bits 7-2k / 6-2k of every byte)
+                    uint32_t best = 0xffffffffu;
+                    for (uint32_t q = r; q; q &= q - 1) {
+                        const int e = __ffs(q) - 1, b = e >> 3, qq = e & 7;
+                        const uint32_t pos = 8 * ((7 - qq) >> 1) + b + ((qq & 1) ? 0 : 4);
+                        const uint32_t key = (pos << 5) | (uint32_t)e;
+                        best = key < best ? key : best;
+                    }
+                    r &= ~(1u << (best & 31));
+                    const uint32_t s = 128 * lane + 32 * gq + (best >> 5);
+                    if (idx >= round && idx < round + kSurvivorCap) surv[idx - round] = (uint16_t)s;
+                    idx++;
                 }
-                keep[h] = k;
             }
-            uint32_t cnt = __popc(keep[0]) + __popc(keep[1]);
-            uint32_t incl = cnt;
+            __syncwarp();
+            const uint32_t n_here = (n_surv - round) < (uint32_t)kSurvivorCap ? (n_surv - round) : (uint32_t)kSurvivorCap;
+            for (uint32_t i = lane; i < n_here; i += 32) {
+                const int s = surv[i];
+                const uint64_t v = (uint64_t)v_tile + s;
+                const bool valid = v >= 2 && (v - 2) < t_end && (((uint32_t)(v - 2)) & (kBufSamples - 1)) < kScanLimit;
+                if (!valid) continue;
+                const int m0 = staged_mag(st, s, lutn), m2 = staged_mag(st, s + 2, lutn);
+                const int m7 = staged_mag(st, s + 7, lutn), m9 = staged_mag(st, s + 9, lutn);
+                const int high = (m0 + m2 + m7 + m9) / 6;                        // dump1090.c:1624
+                if (staged_mag(st, s + 4, lutn) >= high || staged_mag(st, s + 5, lutn) >= high) continue;
+                if (staged_mag(st, s + 11, lutn) >= high || staged_mag(st, s + 12, lutn) >= high ||
+                    staged_mag(st, s + 13, lutn) >= high || staged_mag(st, s + 14, lutn) >= high) continue;
+                atomicOr(&nat[s >> 5], 1u << (s & 31));
+            }
+            __syncwarp();
+        }
+
+        // ---- ordered emission: one atomic per tile
+        {
+            const uint32_t k0 = nat[4 * lane], k1 = nat[4 * lane + 1], k2 = nat[4 * lane + 2], k3 = nat[4 * lane + 3];
+            const uint32_t keep[4] = {k0, k1, k2, k3};
+            uint32_t pc = __popc(k0) + __popc(k1) + __popc(k2) + __popc(k3);
+            uint32_t inc2 = pc;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
+                uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
+                if (lane >= d) inc2 += o;
             }
-            uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t total = __shfl_sync(0xffffffffu, inc2, 31);
             uint32_t base = 0;
             if (lane == 0 && total) base = atomicAdd(&out.counters[0], total);
             base = __shfl_sync(0xffffffffu, base, 0);
-            uint32_t idx = base + incl - cnt;
-            const uint32_t vbase = (uint32_t)(chunk0 * 8) + 64 * lane;
+            uint32_t idx = base + inc2 - pc;
 #pragma unroll
-            for (int h = 0; h < 2; h++)
+            for (int h = 0; h < 4; h++)
                 for (uint32_t r = keep[h]; r; r &= r - 1) {
-                    if (idx < out.cand_capacity) out.cand_v[idx] = vbase + 32 * h + (__ffs(r) - 1);
+                    if (idx < out.cand_capacity) out.cand_v[idx] = v_tile + 128 * lane + 32 * h + (__ffs(r) - 1);
                     idx++;
                 }
             if (lane == 0) {
@@ -181,19 +293,24 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                     out.counters[1] = 1;
                 }
                 modes_tile tl; tl.offset = base; tl.count = stored;
-                out.tiles[tile] = tl;
+                out.tiles[g] = tl;
             }
         }
-        raw = nxt;
+        __syncwarp();                                    // this stage and nat[] are reused two tiles on
     }
 }
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream) {
-    uint32_t n_tiles = tiles_for(in.n_samples);
-    uint32_t grid = (uint32_t)sm_count * 6;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanWarpSmem);
+        attr_set = true;
+    }
+    const uint32_t n_tiles = tiles_for(in.n_samples);
+    uint32_t grid = (uint32_t)sm_count * 11;             // 11 single-warp CTAs fit one SM's shared memory
     if (grid > n_tiles) grid = n_tiles;
-    scan_kernel<<<grid, kScanThreads, 0, stream>>>(in, tab.lutn, out, n_tiles);
+    scan_kernel<<<grid, 32, kScanWarpSmem, stream>>>(in, tab.lutn, out, n_tiles);
 }
 
 // ------------------------------------------------------- K2: frame evaluation

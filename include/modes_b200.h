@@ -102,7 +102,7 @@ typedef struct modes_candidate {
 /* Per scan tile: where its candidates sit in the candidate array.  Tiles are
  * in stream order; candidates inside a tile are in stream order. */
 typedef struct modes_tile { uint32_t offset, count; } modes_tile;
-#define MODES_TILE_SAMPLES 2048
+#define MODES_TILE_SAMPLES 4096
 
 /* Replaces Modes.stat_* (dump1090.c:186-195) in the order the reference prints
  * them (:2994-3003): valid_preamble, out_of_phase, demodulated, goodcrc,
@@ -151,14 +151,14 @@ int  modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples,
  * bytes preceding d_iq (host memory), or NULL at stream start (no-signal).
  * Launches the scan and frame-evaluation kernels on the context's stream and
  * returns without waiting.  d_candidates (capacity cand_capacity records) and
- * d_tiles (n_buffers*64+1 entries) are device memory supplied by the caller, or
+ * d_tiles (n_buffers*32+1 entries) are device memory supplied by the caller, or
  * NULL to use the context's own workspace. */
 int  modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, const uint8_t *carry476,
                          void *d_candidates, size_t cand_capacity, void *d_tiles);
 /* Wait for the last modes_detect_device; returns the candidate count. */
 int  modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates);
 /* Copy the last result to host memory (arrays sized by the caller from
- * modes_detect_wait's count and n_buffers*64+1 tiles). */
+ * modes_detect_wait's count and n_buffers*32+1 tiles). */
 int  modes_detect_fetch(modes_ctx *ctx, modes_candidate *candidates, modes_tile *tiles);
 
 /* The sequential half of detectModeS(): retry/skip state machine
