@@ -100,7 +100,7 @@ constexpr int kStripPitch16 = 17;                        // 272-byte pitch in 16
 constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
 constexpr int kStageBytes = (32 * kStripPitch16 + 3) * 16;   // 8752: 32 strips + 3 lookahead chunks
 constexpr int kSurvivorCap = 512;
-constexpr int kScanWarpSmem = 2 * kStageBytes + 128 * 4 + kSurvivorCap * 2;
+constexpr int kScanWarpSmem = 2 * kStageBytes + 128 * 4 + kSurvivorCap * 2 + 16;
 constexpr uint32_t kK15 = 0x7fff7fffu;
 static_assert(kTileSamples == 32 * kStripSamples, "tile = 32 strips");
 
@@ -150,11 +150,24 @@ __device__ __forceinline__ int staged_mag(const uint8_t *stage, int s, const uin
     return __ldg(lutn + __dp4a(a, a, 0u));
 }
 
+// dump1090.c:1624-1642 for tile-local position s, on exact magnitudes.  All ten
+// loads are issued before any is used (no early exit: latency, not work, is the cost here).
+__device__ __forceinline__ bool high_tests(const uint8_t *stage, int s, const uint16_t *__restrict__ lutn) {
+    const int m0 = staged_mag(stage, s, lutn), m2 = staged_mag(stage, s + 2, lutn);
+    const int m7 = staged_mag(stage, s + 7, lutn), m9 = staged_mag(stage, s + 9, lutn);
+    const int m4 = staged_mag(stage, s + 4, lutn), m5 = staged_mag(stage, s + 5, lutn);
+    const int m11 = staged_mag(stage, s + 11, lutn), m12 = staged_mag(stage, s + 12, lutn);
+    const int m13 = staged_mag(stage, s + 13, lutn), m14 = staged_mag(stage, s + 14, lutn);
+    const int high = (m0 + m2 + m7 + m9) / 6;
+    return (m4 < high) & (m5 < high) & (m11 < high) & (m12 < high) & (m13 < high) & (m14 < high);
+}
+
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint32_t *nat = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes);          // 4096 pass bits, natural order
     uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + 512);   // survivor positions
+    uint32_t *surv_count = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes + 512 + kSurvivorCap * 2);
 
     const int lane = threadIdx.x;
     const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
@@ -209,60 +222,54 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                 const uint32_t D1 = A + cB, D2 = P[w] + cW, D3 = S4 + cE, D4 = S3 + cP4;
                 T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2w / 2w+1 passes
             }
-            // collect the 8 pass flags of this chunk (scrambled order, see decode below)
-            const int k = c & 3;
+            // the 8 pass flags of this chunk as one byte, bit p = position 8c+p: PRMT lines the
+            // flag bytes up in position order, a multiply gathers bit 7 of each byte
             const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
-            acc[c >> 2] |= ((X >> (2 * k)) & (0x80808080u >> (2 * k))) | ((Y >> (2 * k + 1)) & (0x40404040u >> (2 * k)));
+            const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
+            const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
+            acc[c >> 2] |= (lo4 | (hi4 & 0xf0u)) << (8 * (c & 3));
         }
 
-        // ---- survivors -> compact list (tile order), dropping positions the reference never tests
+        // ---- survivors of the ten comparisons (~1% of positions) get the exact "high" tests
+        // (dump1090.c:1624-1642), spread evenly over the warp through a small list
         nat[4 * lane + 0] = 0; nat[4 * lane + 1] = 0; nat[4 * lane + 2] = 0; nat[4 * lane + 3] = 0;
+        if (lane == 0) *surv_count = 0;
         const uint32_t v_tile = g * (uint32_t)kTileSamples;
-        uint32_t cnt = __popc(acc[0]) + __popc(acc[1]) + __popc(acc[2]) + __popc(acc[3]);
-        uint32_t incl = cnt;
+        // positions the reference never tests (dump1090.c:1593): j >= 131070 are the first two
+        // positions of every 32nd tile (v = t+2); the last tile ends at t = N-1
+        const int s_min = (g & 31u) == 0 ? 2 : 0;
+        const uint64_t v_stop = t_end + 2;
+        const int s_max = (v_stop - v_tile) < (uint64_t)kTileSamples ? (int)(v_stop - v_tile) : kTileSamples;
+        __syncwarp();
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31);
-        for (uint32_t round = 0; round < n_surv; round += kSurvivorCap) {
-            uint32_t idx = incl - cnt;                   // this lane's first slot in tile order
-#pragma unroll
-            for (int gq = 0; gq < 4; gq++) {
-                // ascending position order inside the word: chunk k, then position p
-                for (uint32_t r = acc[gq]; r;) {
-                    // lowest position first: scan chunks k=0..3 (bits 7-2k / 6-2k of every byte)
-                    uint32_t best = 0xffffffffu;
-                    for (uint32_t q = r; q; q &= q - 1) {
-                        const int e = __ffs(q) - 1, b = e >> 3, qq = e & 7;
-                        const uint32_t pos = 8 * ((7 - qq) >> 1) + b + ((qq & 1) ? 0 : 4);
-                        const uint32_t key = (pos << 5) | (uint32_t)e;
-                        best = key < best ? key : best;
-                    }
-                    r &= ~(1u << (best & 31));
-                    const uint32_t s = 128 * lane + 32 * gq + (best >> 5);
-                    if (idx >= round && idx < round + kSurvivorCap) surv[idx - round] = (uint16_t)s;
-                    idx++;
+        for (int gq = 0; gq < 4; gq++)
+            for (uint32_t r = acc[gq]; r; r &= r - 1) {
+                const int s = 128 * lane + 32 * gq + (__ffs(r) - 1);
+                if (s >= s_min && s < s_max) {
+                    const uint32_t slot = atomicAdd(surv_count, 1u);
+                    if (slot < (uint32_t)kSurvivorCap) surv[slot] = (uint16_t)s;
                 }
             }
-            __syncwarp();
-            const uint32_t n_here = (n_surv - round) < (uint32_t)kSurvivorCap ? (n_surv - round) : (uint32_t)kSurvivorCap;
-            for (uint32_t i = lane; i < n_here; i += 32) {
+        __syncwarp();
+        const uint32_t n_surv = *surv_count;
+        if (n_surv <= (uint32_t)kSurvivorCap) {
+            for (uint32_t i = lane; i < n_surv; i += 32) {
                 const int s = surv[i];
-                const uint64_t v = (uint64_t)v_tile + s;
-                const bool valid = v >= 2 && (v - 2) < t_end && (((uint32_t)(v - 2)) & (kBufSamples - 1)) < kScanLimit;
-                if (!valid) continue;
-                const int m0 = staged_mag(st, s, lutn), m2 = staged_mag(st, s + 2, lutn);
-                const int m7 = staged_mag(st, s + 7, lutn), m9 = staged_mag(st, s + 9, lutn);
-                const int high = (m0 + m2 + m7 + m9) / 6;                        // dump1090.c:1624
-                if (staged_mag(st, s + 4, lutn) >= high || staged_mag(st, s + 5, lutn) >= high) continue;
-                if (staged_mag(st, s + 11, lutn) >= high || staged_mag(st, s + 12, lutn) >= high ||
-                    staged_mag(st, s + 13, lutn) >= high || staged_mag(st, s + 14, lutn) >= high) continue;
-                atomicOr(&nat[s >> 5], 1u << (s & 31));
+                if (high_tests(st, s, lutn)) atomicOr(&nat[s >> 5], 1u << (s & 31));
             }
-            __syncwarp();
+        } else {
+            // pathological density: every lane tests its own survivors
+#pragma unroll
+            for (int gq = 0; gq < 4; gq++) {
+                uint32_t keepw = 0;
+                for (uint32_t r = acc[gq]; r; r &= r - 1) {
+                    const int bit = __ffs(r) - 1, s = 128 * lane + 32 * gq + bit;
+                    if (s >= s_min && s < s_max && high_tests(st, s, lutn)) keepw |= 1u << bit;
+                }
+                nat[4 * lane + gq] = keepw;
+            }
         }
+        __syncwarp();
 
         // ---- ordered emission: one atomic per tile
         {
@@ -515,16 +522,43 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
 
         // magnitudes: 17 preamble samples m[-1..15] (lane p holds m[p-1]) and 112 (low, high) pairs
         int pm = 0;
-        if (lane < 17) pm = __ldg(tab.lutn + sample_n(in, (uint64_t)v - 1 + lane));
         int lo[4], hi[4];
+        if (v > (uint32_t)kHaloSamples) {
+            // The whole window m[-1..239] lies in the body: 32-bit aligned loads from one base.
+            // Window sample w (w = 0 is m[-1]) is halfword w + odd of the aligned word array.
+            const uint32_t first = v - 1 - kHaloSamples;                 // body sample index of m[-1]
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(in.body) + (first >> 1);
+            const uint32_t odd = first & 1u;
+            if (lane < 17) {
+                const uint32_t h = lane + odd, w = __ldg(wp + (h >> 1));
+                const uint32_t a = __vabsdiffu4(((h & 1u) ? (w >> 16) : (w & 0xffffu)) | 0x7f7f0000u, 0x7f7f7f7fu);
+                pm = __ldg(tab.lutn + __dp4a(a, a, 0u));
+            }
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            int b = 32 * r + lane;
-            lo[r] = 0; hi[r] = 0;
-            if (b < 112) {
-                uint64_t s = (uint64_t)v + 16 + 2 * b;
-                lo[r] = __ldg(tab.lutn + sample_n(in, s));
-                hi[r] = __ldg(tab.lutn + sample_n(in, s + 1));
+            for (int r = 0; r < 4; r++) {
+                const int b = 32 * r + lane;
+                lo[r] = 0; hi[r] = 0;
+                if (b < 112) {
+                    // low = window sample 17+2b, high = 18+2b
+                    const uint32_t wa = __ldg(wp + 8 + b), wb = __ldg(wp + 9 + b);
+                    const uint32_t pair = odd ? wb : __byte_perm(wa, wb, 0x5432);
+                    const uint32_t a = __vabsdiffu4(pair, 0x7f7f7f7fu);
+                    lo[r] = __ldg(tab.lutn + __dp4a(a & 0x0000ffffu, a, 0u));
+                    hi[r] = __ldg(tab.lutn + __dp4a(a & 0xffff0000u, a, 0u));
+                }
+            }
+        } else {
+            // window reaches into the carry block (first 240 positions of a batch)
+            if (lane < 17) pm = __ldg(tab.lutn + sample_n(in, (uint64_t)v - 1 + lane));
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int b = 32 * r + lane;
+                lo[r] = 0; hi[r] = 0;
+                if (b < 112) {
+                    const uint64_t sidx = (uint64_t)v + 16 + 2 * b;
+                    lo[r] = __ldg(tab.lutn + sample_n(in, sidx));
+                    hi[r] = __ldg(tab.lutn + sample_n(in, sidx + 1));
+                }
             }
         }
         // sums for the delta gate, on the uncorrected samples (dump1090.c:1692-1693, :1713-1718)
