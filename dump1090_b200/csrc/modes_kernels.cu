@@ -100,7 +100,7 @@ constexpr int kStripPitch16 = 17;                        // 272-byte pitch in 16
 constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
 constexpr int kStageBytes = (32 * kStripPitch16 + 3) * 16;   // 8752: 32 strips + 3 lookahead chunks
 constexpr int kSurvivorCap = 512;
-constexpr int kScanWarpSmem = 2 * kStageBytes + 128 * 4 + kSurvivorCap * 2 + 16;
+constexpr int kScanWarpSmem = 2 * kStageBytes + 2 * 128 * 4 + kSurvivorCap * 2;
 constexpr uint32_t kK15 = 0x7fff7fffu;
 static_assert(kTileSamples == 32 * kStripSamples, "tile = 32 strips");
 
@@ -162,12 +162,36 @@ __device__ __forceinline__ bool high_tests(const uint8_t *stage, int s, const ui
     return (m4 < high) & (m5 < high) & (m11 < high) & (m12 < high) & (m13 < high) & (m14 < high);
 }
 
+// Write one tile's candidates (pass bits in natural order, 4 words per lane) at the slot
+// obtained from the global counter, in position order; record the tile in the tile table.
+__device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint32_t *natw, uint32_t tile, uint32_t base0,
+                                          uint32_t excl, uint32_t total, int lane) {
+    const uint32_t base = __shfl_sync(0xffffffffu, base0, 0);
+    uint32_t idx = base + excl;
+    const uint32_t v0 = tile * (uint32_t)kTileSamples + 128 * lane;
+#pragma unroll
+    for (int h = 0; h < 4; h++)
+        for (uint32_t r = natw[4 * lane + h]; r; r &= r - 1) {
+            if (idx < out.cand_capacity) out.cand_v[idx] = v0 + 32 * h + (__ffs(r) - 1);
+            idx++;
+        }
+    if (lane == 0) {
+        uint32_t stored = total;
+        if (base + total > out.cand_capacity) {
+            stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
+            out.counters[1] = 1;
+        }
+        modes_tile tl; tl.offset = base; tl.count = stored;
+        out.tiles[tile] = tl;
+    }
+}
+
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t *nat = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes);          // 4096 pass bits, natural order
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + 512);   // survivor positions
-    uint32_t *surv_count = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes + 512 + kSurvivorCap * 2);
+    uint32_t *nat = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes);          // 2 x 4096 pass bits, natural order
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + 1024);  // survivor positions
+    uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_excl = 0, pend_total = 0;
 
     const int lane = threadIdx.x;
     const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
@@ -230,32 +254,47 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             acc[c >> 2] |= (lo4 | (hi4 & 0xf0u)) << (8 * (c & 3));
         }
 
+        // ---- emit the PREVIOUS tile's candidates: its global slot (one atomic per tile) was
+        // requested before this tile's strip scan, so the round trip is hidden behind it
+        if (it > 0) emit_tile(out, nat + 128 * (cur ^ 1), pend_tile, pend_base, pend_excl, pend_total, lane);
+
         // ---- survivors of the ten comparisons (~1% of positions) get the exact "high" tests
         // (dump1090.c:1624-1642), spread evenly over the warp through a small list
-        nat[4 * lane + 0] = 0; nat[4 * lane + 1] = 0; nat[4 * lane + 2] = 0; nat[4 * lane + 3] = 0;
-        if (lane == 0) *surv_count = 0;
+        uint32_t *natc = nat + 128 * cur;
+        natc[4 * lane + 0] = 0; natc[4 * lane + 1] = 0; natc[4 * lane + 2] = 0; natc[4 * lane + 3] = 0;
         const uint32_t v_tile = g * (uint32_t)kTileSamples;
         // positions the reference never tests (dump1090.c:1593): j >= 131070 are the first two
         // positions of every 32nd tile (v = t+2); the last tile ends at t = N-1
-        const int s_min = (g & 31u) == 0 ? 2 : 0;
-        const uint64_t v_stop = t_end + 2;
-        const int s_max = (v_stop - v_tile) < (uint64_t)kTileSamples ? (int)(v_stop - v_tile) : kTileSamples;
-        __syncwarp();
+        if ((g & 31u) == 0 && lane == 0) acc[0] &= ~3u;
+        {
+            const uint64_t v_stop = t_end + 2;
+            if (v_stop - v_tile < (uint64_t)kTileSamples) {
+                const int s_max = (int)(v_stop - v_tile);
 #pragma unroll
-        for (int gq = 0; gq < 4; gq++)
-            for (uint32_t r = acc[gq]; r; r &= r - 1) {
-                const int s = 128 * lane + 32 * gq + (__ffs(r) - 1);
-                if (s >= s_min && s < s_max) {
-                    const uint32_t slot = atomicAdd(surv_count, 1u);
-                    if (slot < (uint32_t)kSurvivorCap) surv[slot] = (uint16_t)s;
+                for (int gq = 0; gq < 4; gq++) {
+                    const int lo_pos = 128 * lane + 32 * gq;
+                    if (lo_pos >= s_max) acc[gq] = 0;
+                    else if (lo_pos + 32 > s_max) acc[gq] &= (1u << (s_max - lo_pos)) - 1u;
                 }
             }
-        __syncwarp();
-        const uint32_t n_surv = *surv_count;
+        }
+        const uint32_t cnt = __popc(acc[0]) + __popc(acc[1]) + __popc(acc[2]) + __popc(acc[3]);
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += o;
+        }
+        const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31);
         if (n_surv <= (uint32_t)kSurvivorCap) {
+            uint32_t slot = incl - cnt;
+            uint64_t w01 = acc[0] | ((uint64_t)acc[1] << 32), w23 = acc[2] | ((uint64_t)acc[3] << 32);
+            while (w01) { surv[slot++] = (uint16_t)(128 * lane + __ffsll((long long)w01) - 1); w01 &= w01 - 1; }
+            while (w23) { surv[slot++] = (uint16_t)(128 * lane + 64 + __ffsll((long long)w23) - 1); w23 &= w23 - 1; }
+            __syncwarp();
             for (uint32_t i = lane; i < n_surv; i += 32) {
-                const int s = surv[i];
-                if (high_tests(st, s, lutn)) atomicOr(&nat[s >> 5], 1u << (s & 31));
+                const int sp_ = surv[i];
+                if (high_tests(st, sp_, lutn)) atomicOr(&natc[sp_ >> 5], 1u << (sp_ & 31));
             }
         } else {
             // pathological density: every lane tests its own survivors
@@ -263,48 +302,34 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             for (int gq = 0; gq < 4; gq++) {
                 uint32_t keepw = 0;
                 for (uint32_t r = acc[gq]; r; r &= r - 1) {
-                    const int bit = __ffs(r) - 1, s = 128 * lane + 32 * gq + bit;
-                    if (s >= s_min && s < s_max && high_tests(st, s, lutn)) keepw |= 1u << bit;
+                    const int bit = __ffs(r) - 1;
+                    if (high_tests(st, 128 * lane + 32 * gq + bit, lutn)) keepw |= 1u << bit;
                 }
-                nat[4 * lane + gq] = keepw;
+                natc[4 * lane + gq] = keepw;
             }
         }
         __syncwarp();
 
-        // ---- ordered emission: one atomic per tile
+        // ---- request this tile's slot in the candidate array; the write-out happens one tile later
         {
-            const uint32_t k0 = nat[4 * lane], k1 = nat[4 * lane + 1], k2 = nat[4 * lane + 2], k3 = nat[4 * lane + 3];
-            const uint32_t keep[4] = {k0, k1, k2, k3};
-            uint32_t pc = __popc(k0) + __popc(k1) + __popc(k2) + __popc(k3);
+            const uint32_t pc = __popc(natc[4 * lane]) + __popc(natc[4 * lane + 1]) + __popc(natc[4 * lane + 2]) +
+                                __popc(natc[4 * lane + 3]);
             uint32_t inc2 = pc;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
                 if (lane >= d) inc2 += o;
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, inc2, 31);
-            uint32_t base = 0;
-            if (lane == 0 && total) base = atomicAdd(&out.counters[0], total);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            uint32_t idx = base + inc2 - pc;
-#pragma unroll
-            for (int h = 0; h < 4; h++)
-                for (uint32_t r = keep[h]; r; r &= r - 1) {
-                    if (idx < out.cand_capacity) out.cand_v[idx] = v_tile + 128 * lane + 32 * h + (__ffs(r) - 1);
-                    idx++;
-                }
-            if (lane == 0) {
-                uint32_t stored = total;
-                if (base + total > out.cand_capacity) {
-                    stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
-                    out.counters[1] = 1;
-                }
-                modes_tile tl; tl.offset = base; tl.count = stored;
-                out.tiles[g] = tl;
-            }
+            pend_total = __shfl_sync(0xffffffffu, inc2, 31);
+            pend_excl = inc2 - pc;
+            pend_base = 0;
+            if (lane == 0 && pend_total) pend_base = atomicAdd(&out.counters[0], pend_total);
+            pend_tile = g;
         }
-        __syncwarp();                                    // this stage and nat[] are reused two tiles on
     }
+    // the last tile of this warp
+    if (pend_tile != 0xffffffffu)
+        emit_tile(out, nat + 128 * (((pend_tile - blockIdx.x) / gridDim.x) & 1), pend_tile, pend_base, pend_excl, pend_total, lane);
 }
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
@@ -501,6 +526,25 @@ __device__ __forceinline__ void eval_words(const PassResult &R, uint32_t w[6]) {
 
 constexpr int kEvalThreads = 256;
 
+// Raw 32-bit words of one candidate's window m[-1..239] as held by one lane: window sample w
+// (w = 0 is m[-1]) is halfword w + odd of the aligned word array starting at body sample
+// (v-241) & ~1; bit b = 32r+lane needs words 8+b and 9+b, the preamble lanes word (lane+odd)/2.
+struct RawWindow { uint32_t v, pw, wa[4], wb[4]; };
+
+__device__ __forceinline__ void load_window(const BatchView &in, uint32_t v, int lane, RawWindow &w) {
+    w.v = v;
+    if (v <= (uint32_t)kHaloSamples) return;             // carry-block window: loaded on demand
+    const uint32_t first = v - 1 - kHaloSamples;         // body sample index of m[-1]
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(in.body) + (first >> 1);
+    w.pw = (lane < 17) ? __ldg(wp + ((lane + (first & 1u)) >> 1)) : 0u;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int b = 32 * r + lane;
+        w.wa[r] = 0; w.wb[r] = 0;
+        if (b < 112) { w.wa[r] = __ldg(wp + 8 + b); w.wb[r] = __ldg(wp + 9 + b); }
+    }
+}
+
 __global__ void __launch_bounds__(kEvalThreads)
 eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, const uint32_t *counters,
             uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
@@ -515,33 +559,36 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
     uint32_t n_cand = counters[0];
     if (n_cand > cand_capacity) n_cand = cand_capacity;
 
-    for (uint32_t ci = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ci < n_cand;
-         ci += gridDim.x * warps_per_block) {
-        const uint32_t v = cand_v[ci];
+    // Software pipeline: the raw words of the next candidate are requested before this one is
+    // evaluated, so the HBM round trip (cand_v -> I/Q words) overlaps a full evaluation.
+    const uint32_t stride = gridDim.x * warps_per_block;
+    uint32_t ci = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    RawWindow cur;
+    if (ci < n_cand) load_window(in, cand_v[ci], lane, cur);
+    for (; ci < n_cand; ci += stride) {
+        RawWindow nxt;
+        nxt.v = 0;
+        if (ci + stride < n_cand) load_window(in, cand_v[ci + stride], lane, nxt);
+
+        const uint32_t v = cur.v;
         const uint64_t t = (uint64_t)v - 2;
 
         // magnitudes: 17 preamble samples m[-1..15] (lane p holds m[p-1]) and 112 (low, high) pairs
         int pm = 0;
         int lo[4], hi[4];
         if (v > (uint32_t)kHaloSamples) {
-            // The whole window m[-1..239] lies in the body: 32-bit aligned loads from one base.
-            // Window sample w (w = 0 is m[-1]) is halfword w + odd of the aligned word array.
-            const uint32_t first = v - 1 - kHaloSamples;                 // body sample index of m[-1]
-            const uint32_t *wp = reinterpret_cast<const uint32_t *>(in.body) + (first >> 1);
-            const uint32_t odd = first & 1u;
+            const uint32_t odd = (v - 1 - kHaloSamples) & 1u;
             if (lane < 17) {
-                const uint32_t h = lane + odd, w = __ldg(wp + (h >> 1));
-                const uint32_t a = __vabsdiffu4(((h & 1u) ? (w >> 16) : (w & 0xffffu)) | 0x7f7f0000u, 0x7f7f7f7fu);
+                const uint32_t h = lane + odd;
+                const uint32_t a = __vabsdiffu4(((h & 1u) ? (cur.pw >> 16) : (cur.pw & 0xffffu)) | 0x7f7f0000u, 0x7f7f7f7fu);
                 pm = __ldg(tab.lutn + __dp4a(a, a, 0u));
             }
 #pragma unroll
             for (int r = 0; r < 4; r++) {
-                const int b = 32 * r + lane;
                 lo[r] = 0; hi[r] = 0;
-                if (b < 112) {
+                if (32 * r + lane < 112) {
                     // low = window sample 17+2b, high = 18+2b
-                    const uint32_t wa = __ldg(wp + 8 + b), wb = __ldg(wp + 9 + b);
-                    const uint32_t pair = odd ? wb : __byte_perm(wa, wb, 0x5432);
+                    const uint32_t pair = odd ? cur.wb[r] : __byte_perm(cur.wa[r], cur.wb[r], 0x5432);
                     const uint32_t a = __vabsdiffu4(pair, 0x7f7f7f7fu);
                     lo[r] = __ldg(tab.lutn + __dp4a(a & 0x0000ffffu, a, 0u));
                     hi[r] = __ldg(tab.lutn + __dp4a(a & 0xffff0000u, a, 0u));
@@ -656,6 +703,7 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
 #pragma unroll
         for (int k = 0; k < 14; k++) word = (lane == k) ? rec[k] : word;
         if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = word;
+        cur = nxt;
     }
 }
 
