@@ -100,7 +100,8 @@ constexpr int kStripPitch16 = 17;                        // 272-byte pitch in 16
 constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
 constexpr int kStageBytes = (32 * kStripPitch16 + 3) * 16;   // 8752: 32 strips + 3 lookahead chunks
 constexpr int kSurvivorCap = 512;
-constexpr int kScanWarpSmem = 2 * kStageBytes + 2 * 128 * 4 + kSurvivorCap * 2;
+constexpr int kOutCap = 256;                             // candidates per tile held back one tile
+constexpr int kScanWarpSmem = 2 * kStageBytes + kSurvivorCap * 2 + 2 * kOutCap * 2;
 constexpr uint32_t kK15 = 0x7fff7fffu;
 static_assert(kTileSamples == 32 * kStripSamples, "tile = 32 strips");
 
@@ -143,38 +144,55 @@ __device__ __forceinline__ void stage_tile(const BatchView &in, uint32_t stage_a
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-// Magnitude of sample s (tile-local, 0..4119) from the staged raw bytes.
-__device__ __forceinline__ int staged_mag(const uint8_t *stage, int s, const uint16_t *__restrict__ lutn) {
-    uint32_t w = *reinterpret_cast<const uint16_t *>(stage + (s >> 7) * (kStripPitch16 * 16) + (s & 127) * 2);
-    uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
-    return __ldg(lutn + __dp4a(a, a, 0u));
+// Squared magnitude of the sample `d` positions after the one at `p0` (staged raw bytes);
+// `dc` = number of samples left in p0's strip (the next strip starts 16 pad bytes later).
+__device__ __forceinline__ uint32_t staged_n(const uint8_t *p0, int d, int dc) {
+    const uint32_t w = *reinterpret_cast<const uint16_t *>(p0 + 2 * d + (d >= dc ? 16 : 0));
+    const uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
+    return __dp4a(a, a, 0u);
 }
 
-// dump1090.c:1624-1642 for tile-local position s, on exact magnitudes.  All ten
-// loads are issued before any is used (no early exit: latency, not work, is the cost here).
+// dump1090.c:1624-1642 for tile-local position s, on exact magnitudes:
+//   high = (m0+m2+m7+m9)/6;  m4, m5, m11..m14 < high
+// <=> 6*(max(m4,m5,m11..m14)+1) <= m0+m2+m7+m9, and the magnitude table is monotone in the
+// squared magnitude, so the max is taken before the lookup: five lookups instead of ten.
 __device__ __forceinline__ bool high_tests(const uint8_t *stage, int s, const uint16_t *__restrict__ lutn) {
-    const int m0 = staged_mag(stage, s, lutn), m2 = staged_mag(stage, s + 2, lutn);
-    const int m7 = staged_mag(stage, s + 7, lutn), m9 = staged_mag(stage, s + 9, lutn);
-    const int m4 = staged_mag(stage, s + 4, lutn), m5 = staged_mag(stage, s + 5, lutn);
-    const int m11 = staged_mag(stage, s + 11, lutn), m12 = staged_mag(stage, s + 12, lutn);
-    const int m13 = staged_mag(stage, s + 13, lutn), m14 = staged_mag(stage, s + 14, lutn);
-    const int high = (m0 + m2 + m7 + m9) / 6;
-    return (m4 < high) & (m5 < high) & (m11 < high) & (m12 < high) & (m13 < high) & (m14 < high);
+    const int o = s & 127, dc = 128 - o;
+    const uint8_t *p0 = stage + (s >> 7) * (kStripPitch16 * 16) + 2 * o;
+    const uint32_t n0 = staged_n(p0, 0, dc), n2 = staged_n(p0, 2, dc), n7 = staged_n(p0, 7, dc), n9 = staged_n(p0, 9, dc);
+    const uint32_t n4 = staged_n(p0, 4, dc), n5 = staged_n(p0, 5, dc), n11 = staged_n(p0, 11, dc);
+    const uint32_t n12 = staged_n(p0, 12, dc), n13 = staged_n(p0, 13, dc), n14 = staged_n(p0, 14, dc);
+    const uint32_t nx = max(max(max(n4, n5), max(n11, n12)), max(n13, n14));
+    const int sum = (int)__ldg(lutn + n0) + (int)__ldg(lutn + n2) + (int)__ldg(lutn + n7) + (int)__ldg(lutn + n9);
+    const int mx = __ldg(lutn + nx);
+    return 6 * (mx + 1) <= sum;
 }
 
-// Write one tile's candidates (pass bits in natural order, 4 words per lane) at the slot
-// obtained from the global counter, in position order; record the tile in the tile table.
-__device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint32_t *natw, uint32_t tile, uint32_t base0,
-                                          uint32_t excl, uint32_t total, int lane) {
+// One lane's survivors (bits of acc[4], bit i of word g = strip position 32g+i) -> the slots
+// [excl, excl+cnt) of the tile-ordered survivor sequence; writes those that fall in
+// [round, round+kSurvivorCap) to the list.
+__device__ __forceinline__ void list_survivors(const uint32_t acc[4], uint32_t excl, uint32_t round, uint16_t *surv,
+                                               int lane) {
+    uint32_t slot = excl;
+    uint64_t w01 = acc[0] | ((uint64_t)acc[1] << 32), w23 = acc[2] | ((uint64_t)acc[3] << 32);
+    while (w01) {
+        if (slot - round < (uint32_t)kSurvivorCap) surv[slot - round] = (uint16_t)(128 * lane + __ffsll((long long)w01) - 1);
+        slot++; w01 &= w01 - 1;
+    }
+    while (w23) {
+        if (slot - round < (uint32_t)kSurvivorCap) surv[slot - round] = (uint16_t)(128 * lane + 64 + __ffsll((long long)w23) - 1);
+        slot++; w23 &= w23 - 1;
+    }
+}
+
+// Copy a finished tile's candidate list (tile-local positions, position order) to its slot in the
+// global candidate array and record the tile.  `base0` is the slot claimed one tile earlier.
+__device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t *olist, uint32_t tile, uint32_t base0,
+                                          uint32_t total, int lane) {
     const uint32_t base = __shfl_sync(0xffffffffu, base0, 0);
-    uint32_t idx = base + excl;
-    const uint32_t v0 = tile * (uint32_t)kTileSamples + 128 * lane;
-#pragma unroll
-    for (int h = 0; h < 4; h++)
-        for (uint32_t r = natw[4 * lane + h]; r; r &= r - 1) {
-            if (idx < out.cand_capacity) out.cand_v[idx] = v0 + 32 * h + (__ffs(r) - 1);
-            idx++;
-        }
+    const uint32_t v0 = tile * (uint32_t)kTileSamples;
+    for (uint32_t i = lane; i < total; i += 32)
+        if (base + i < out.cand_capacity) out.cand_v[base + i] = v0 + olist[i];
     if (lane == 0) {
         uint32_t stored = total;
         if (base + total > out.cand_capacity) {
@@ -189,9 +207,9 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint32_t
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint32_t *nat = reinterpret_cast<uint32_t *>(smem + 2 * kStageBytes);          // 2 x 4096 pass bits, natural order
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + 1024);  // survivor positions
-    uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_excl = 0, pend_total = 0;
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes);                       // survivor positions
+    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + kSurvivorCap * 2);  // 2 x candidate lists
+    uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
 
     const int lane = threadIdx.x;
     const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
@@ -211,73 +229,81 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
         }
         __syncwarp();
 
-        // ---- scan this lane's strip: 16 chunks of 8 positions, rolling window of packed words
+        // ---- scan this lane's strip: 4 x (4 chunks of 8 positions), rolling window of packed words
         const uint8_t *st = smem + cur * kStageBytes;
         const uint4 *sp = reinterpret_cast<const uint4 *>(st) + lane * kStripPitch16;
-        uint32_t P[76];
+        uint32_t P[24];                                  // chunks 4q .. 4q+5 of the strip
         {
             uint4 r0 = sp[0], r1 = sp[1];
             P[0] = n2_pack15(r0.x); P[1] = n2_pack15(r0.y); P[2] = n2_pack15(r0.z); P[3] = n2_pack15(r0.w);
             P[4] = n2_pack15(r1.x); P[5] = n2_pack15(r1.y); P[6] = n2_pack15(r1.z); P[7] = n2_pack15(r1.w);
         }
         uint32_t acc[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
+        for (int q = 0; q < 4; q++) {
+            // squared magnitudes of chunks 4q+2 .. 4q+5 (chunks 16,17 are the next strip's first two)
 #pragma unroll
-        for (int c = 0; c < 16; c++) {
-            {   // squared magnitudes of chunk c+2 (chunks 16,17 are the next strip's first two)
-                const int cc = c + 2;
-                uint4 r = sp[cc < 16 ? cc : cc + 1];
-                P[4 * cc + 0] = n2_pack15(r.x); P[4 * cc + 1] = n2_pack15(r.y);
-                P[4 * cc + 2] = n2_pack15(r.z); P[4 * cc + 3] = n2_pack15(r.w);
+            for (int k = 0; k < 4; k++) {
+                const int cc = 4 * q + 2 + k;
+                const uint4 r = sp[cc + (cc >= 16 ? 1 : 0)];
+                P[8 + 4 * k + 0] = n2_pack15(r.x); P[8 + 4 * k + 1] = n2_pack15(r.y);
+                P[8 + 4 * k + 2] = n2_pack15(r.z); P[8 + 4 * k + 3] = n2_pack15(r.w);
             }
-            uint32_t T[4];
+            uint32_t word = 0;
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int w = 4 * c + u;                 // packed word = positions 2w, 2w+1 of the strip
-                // odd-aligned pairs S[x] = (n[2x+1], n[2x+2]) and complements
-                const uint32_t S0 = __byte_perm(P[w], P[w + 1], 0x5432), S1 = __byte_perm(P[w + 1], P[w + 2], 0x5432);
-                const uint32_t S2 = __byte_perm(P[w + 2], P[w + 3], 0x5432);
-                const uint32_t S3 = __byte_perm(P[w + 3], P[w + 4], 0x5432), S4 = __byte_perm(P[w + 4], P[w + 5], 0x5432);
-                const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
-                const uint32_t cP2 = kK15 - P[w + 2], cP3 = kK15 - P[w + 3], cP4 = kK15 - P[w + 4];
-                const uint32_t A = __vminu2(P[w], P[w + 1]);                   // min(m0, m2)
-                const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
-                const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
-                const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
-                const uint32_t D1 = A + cB, D2 = P[w] + cW, D3 = S4 + cE, D4 = S3 + cP4;
-                T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2w / 2w+1 passes
-            }
-            // the 8 pass flags of this chunk as one byte, bit p = position 8c+p: PRMT lines the
-            // flag bytes up in position order, a multiply gathers bit 7 of each byte
-            const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
-            const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
-            const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
-            acc[c >> 2] |= (lo4 | (hi4 & 0xf0u)) << (8 * (c & 3));
-        }
-
-        // ---- emit the PREVIOUS tile's candidates: its global slot (one atomic per tile) was
-        // requested before this tile's strip scan, so the round trip is hidden behind it
-        if (it > 0) emit_tile(out, nat + 128 * (cur ^ 1), pend_tile, pend_base, pend_excl, pend_total, lane);
-
-        // ---- survivors of the ten comparisons (~1% of positions) get the exact "high" tests
-        // (dump1090.c:1624-1642), spread evenly over the warp through a small list
-        uint32_t *natc = nat + 128 * cur;
-        natc[4 * lane + 0] = 0; natc[4 * lane + 1] = 0; natc[4 * lane + 2] = 0; natc[4 * lane + 3] = 0;
-        const uint32_t v_tile = g * (uint32_t)kTileSamples;
-        // positions the reference never tests (dump1090.c:1593): j >= 131070 are the first two
-        // positions of every 32nd tile (v = t+2); the last tile ends at t = N-1
-        if ((g & 31u) == 0 && lane == 0) acc[0] &= ~3u;
-        {
-            const uint64_t v_stop = t_end + 2;
-            if (v_stop - v_tile < (uint64_t)kTileSamples) {
-                const int s_max = (int)(v_stop - v_tile);
+            for (int c = 0; c < 4; c++) {
+                uint32_t T[4];
 #pragma unroll
-                for (int gq = 0; gq < 4; gq++) {
-                    const int lo_pos = 128 * lane + 32 * gq;
-                    if (lo_pos >= s_max) acc[gq] = 0;
-                    else if (lo_pos + 32 > s_max) acc[gq] &= (1u << (s_max - lo_pos)) - 1u;
+                for (int u = 0; u < 4; u++) {
+                    const int w = 4 * c + u;             // packed word = positions 2w, 2w+1 of this group
+                    // odd-aligned pairs S[x] = (n[2x+1], n[2x+2]) and complements
+                    const uint32_t S0 = __byte_perm(P[w], P[w + 1], 0x5432), S1 = __byte_perm(P[w + 1], P[w + 2], 0x5432);
+                    const uint32_t S2 = __byte_perm(P[w + 2], P[w + 3], 0x5432);
+                    const uint32_t S3 = __byte_perm(P[w + 3], P[w + 4], 0x5432), S4 = __byte_perm(P[w + 4], P[w + 5], 0x5432);
+                    const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
+                    const uint32_t cP2 = kK15 - P[w + 2], cP3 = kK15 - P[w + 3], cP4 = kK15 - P[w + 4];
+                    const uint32_t A = __vminu2(P[w], P[w + 1]);                   // min(m0, m2)
+                    const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
+                    const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
+                    const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
+                    const uint32_t D1 = A + cB, D2 = P[w] + cW, D3 = S4 + cE, D4 = S3 + cP4;
+                    T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2w / 2w+1 passes
                 }
+                // the 8 pass flags of this chunk as one byte, bit p = position 8c+p: PRMT lines the
+                // flag bytes up in position order, a multiply gathers bit 7 of each byte
+                const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
+                const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
+                const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
+                word |= (lo4 | (hi4 & 0xf0u)) << (8 * c);
+            }
+            acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = word;       // after 4 rounds: acc[q] = group q
+#pragma unroll
+            for (int k = 0; k < 8; k++) P[k] = P[16 + k];                           // slide the window by 4 chunks
+        }
+
+        // ---- write out the PREVIOUS tile's candidates: its slot in the global array (one atomic
+        // per tile) was claimed before this tile's strip scan, so the round trip is hidden
+        if (pend_tile != 0xffffffffu) {
+            emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
+            pend_tile = 0xffffffffu;
+        }
+
+        // ---- positions the reference never tests (dump1090.c:1593): j >= 131070 are the first two
+        // positions of every 32nd tile (v = t+2); the last tile ends at t = N-1
+        const uint32_t v_tile = g * (uint32_t)kTileSamples;
+        if ((g & 31u) == 0 && lane == 0) acc[0] &= ~3u;
+        if (t_end + 2 - v_tile < (uint64_t)kTileSamples) {
+            const int s_max = (int)(t_end + 2 - v_tile);
+#pragma unroll
+            for (int gq = 0; gq < 4; gq++) {
+                const int lo_pos = 128 * lane + 32 * gq;
+                if (lo_pos >= s_max) acc[gq] = 0;
+                else if (lo_pos + 32 > s_max) acc[gq] &= (1u << (s_max - lo_pos)) - 1u;
             }
         }
+
+        // ---- survivors of the ten comparisons (~1% of positions) get the exact "high" tests,
+        // 32 at a time in position order; passes are appended to this tile's candidate list
         const uint32_t cnt = __popc(acc[0]) + __popc(acc[1]) + __popc(acc[2]) + __popc(acc[3]);
         uint32_t incl = cnt;
 #pragma unroll
@@ -286,50 +312,69 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             if (lane >= d) incl += o;
         }
         const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31);
-        if (n_surv <= (uint32_t)kSurvivorCap) {
-            uint32_t slot = incl - cnt;
-            uint64_t w01 = acc[0] | ((uint64_t)acc[1] << 32), w23 = acc[2] | ((uint64_t)acc[3] << 32);
-            while (w01) { surv[slot++] = (uint16_t)(128 * lane + __ffsll((long long)w01) - 1); w01 &= w01 - 1; }
-            while (w23) { surv[slot++] = (uint16_t)(128 * lane + 64 + __ffsll((long long)w23) - 1); w23 &= w23 - 1; }
+        uint16_t *olist = olist0 + kOutCap * cur;
+        uint32_t n_out = 0;
+        bool dense = n_surv > (uint32_t)kSurvivorCap;
+        if (!dense) {
+            list_survivors(acc, incl - cnt, 0, surv, lane);
             __syncwarp();
-            for (uint32_t i = lane; i < n_surv; i += 32) {
-                const int sp_ = surv[i];
-                if (high_tests(st, sp_, lutn)) atomicOr(&natc[sp_ >> 5], 1u << (sp_ & 31));
+            for (uint32_t i0 = 0; i0 < n_surv; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                const int spos = i < n_surv ? surv[i] : 0;
+                const bool pass = i < n_surv && high_tests(st, spos, lutn);
+                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                const uint32_t slot = n_out + __popc(bal & ((1u << lane) - 1u));
+                if (pass && slot < (uint32_t)kOutCap) olist[slot] = (uint16_t)spos;
+                n_out += __popc(bal);
             }
-        } else {
-            // pathological density: every lane tests its own survivors
-#pragma unroll
-            for (int gq = 0; gq < 4; gq++) {
-                uint32_t keepw = 0;
-                for (uint32_t r = acc[gq]; r; r &= r - 1) {
-                    const int bit = __ffs(r) - 1;
-                    if (high_tests(st, 128 * lane + 32 * gq + bit, lutn)) keepw |= 1u << bit;
-                }
-                natc[4 * lane + gq] = keepw;
-            }
+            dense = n_out > (uint32_t)kOutCap;
         }
-        __syncwarp();
-
-        // ---- request this tile's slot in the candidate array; the write-out happens one tile later
-        {
-            const uint32_t pc = __popc(natc[4 * lane]) + __popc(natc[4 * lane + 1]) + __popc(natc[4 * lane + 2]) +
-                                __popc(natc[4 * lane + 3]);
-            uint32_t inc2 = pc;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t o = __shfl_up_sync(0xffffffffu, inc2, d);
-                if (lane >= d) inc2 += o;
-            }
-            pend_total = __shfl_sync(0xffffffffu, inc2, 31);
-            pend_excl = inc2 - pc;
+        if (!dense) {
+            // claim the slot now, copy the list one tile later
             pend_base = 0;
-            if (lane == 0 && pend_total) pend_base = atomicAdd(&out.counters[0], pend_total);
-            pend_tile = g;
+            if (lane == 0 && n_out) pend_base = atomicAdd(&out.counters[0], n_out);
+            pend_total = n_out; pend_tile = g; pend_buf = cur;
+        } else {
+            // pathological density: count, claim, then write straight to the global array
+            uint32_t total = 0;
+            for (int pass_no = 0; pass_no < 2; pass_no++) {
+                uint32_t base = 0, run = 0;
+                if (pass_no == 1) {
+                    if (lane == 0 && total) base = atomicAdd(&out.counters[0], total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                }
+                for (uint32_t round = 0; round < n_surv; round += kSurvivorCap) {
+                    __syncwarp();
+                    list_survivors(acc, incl - cnt, round, surv, lane);
+                    __syncwarp();
+                    const uint32_t n_here = min(n_surv - round, (uint32_t)kSurvivorCap);
+                    for (uint32_t i0 = 0; i0 < n_here; i0 += 32) {
+                        const uint32_t i = i0 + lane;
+                        const int spos = i < n_here ? surv[i] : 0;
+                        const bool pass = i < n_here && high_tests(st, spos, lutn);
+                        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+                        if (pass_no == 1 && pass) {
+                            const uint32_t idx = base + run + __popc(bal & ((1u << lane) - 1u));
+                            if (idx < out.cand_capacity) out.cand_v[idx] = v_tile + spos;
+                        }
+                        run += __popc(bal);
+                    }
+                }
+                if (pass_no == 0) total = run;
+                else if (lane == 0) {
+                    uint32_t stored = total;
+                    if (base + total > out.cand_capacity) {
+                        stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
+                        out.counters[1] = 1;
+                    }
+                    modes_tile tl; tl.offset = base; tl.count = stored;
+                    out.tiles[g] = tl;
+                }
+            }
         }
+        __syncwarp();                                    // this stage and the lists are reused later
     }
-    // the last tile of this warp
-    if (pend_tile != 0xffffffffu)
-        emit_tile(out, nat + 128 * (((pend_tile - blockIdx.x) / gridDim.x) & 1), pend_tile, pend_base, pend_excl, pend_total, lane);
+    if (pend_tile != 0xffffffffu) emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
 }
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
