@@ -72,44 +72,34 @@ __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
 
 // ------------------------------------------------------------------ K1: scan
 //
-// "Strip scan".  One warp owns one tile of 4096 positions at a time; lane l walks
-// the 128 consecutive positions [128l, 128l+128) of the tile with a rolling
-// register window, so every sample's squared magnitude and every derived
-// quantity is computed exactly once (plus a 17-sample overlap per strip).
-//
-// Data movement: the tile's raw I/Q (8 KB + 48 B lookahead) is copied
-// global -> shared with cp.async (16 B per lane per instruction, fully
-// coalesced, no register staging), two stages per warp so the next tile streams
-// in while this one is scanned.  In shared memory each 256-byte strip is padded
-// to 272 bytes, which makes the per-lane 16-byte reads of a warp conflict-free.
+// "Row scan".  One warp owns one tile of 4096 positions at a time and walks it in 16
+// rows of 256 positions: in row r lane l handles the 8 positions of chunk 32r+l, so
+// every load is a fully coalesced 512-byte warp read straight from HBM into registers
+// (three rows in flight per warp), with no shared-memory staging at all.  The 17-sample
+// lookahead a position needs comes from the two neighbouring lanes by shuffle (lanes 30
+// and 31 take it from the next row, which is already loaded).  With ~60 registers and
+// 2.5 KB of shared memory per warp, 32 single-warp CTAs fit an SM, which is what hides
+// the latency of the rare exact tests below.
 //
 // Arithmetic: squared magnitudes n = i*i+q*q are held two per 32-bit register as
-// 15-bit fields (n clamped to 32767, order preserving on the reachable values),
-// so one 32-bit instruction works on two positions:
+// 15-bit fields (n clamped to 32767, order preserving on the reachable values), so one
+// 32-bit instruction works on two positions:
 //     cX      = 0x7fff7fff - X          (complement, per half)
 //     L + cR  has bit 15 / bit 31 set   <=>  L > R   in the low / high half
 // The ten comparisons of dump1090.c:1602-1611 for position j reduce to
 //     min(m0,m2) > max(m1,m3)      m0 > max(m4,m5,m6)
 //     m9 > max(m6,m8)              m7 > m8
 // i.e. per pair of positions: 3 packed min, 1 packed min3, 4 adds, 2 ANDs.
-// Survivors (~1% of positions) then get the exact "high" tests
-// (dump1090.c:1624-1642) on magnitudes from the table, balanced across the warp.
+// Survivors (~1% of positions) then get the exact "high" tests (dump1090.c:1624-1642) on
+// magnitudes from the table, 32 at a time in position order; their samples are re-read
+// from L2, where the tile still sits.
 
-constexpr int kStripSamples = 128;                       // per lane per tile
-constexpr int kStripPitch16 = 17;                        // 272-byte pitch in 16-byte units
 constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
-constexpr int kStageBytes = (32 * kStripPitch16 + 3) * 16;   // 8752: 32 strips + 3 lookahead chunks
 constexpr int kSurvivorCap = 512;
 constexpr int kOutCap = 256;                             // candidates per tile held back one tile
-constexpr int kScanWarpSmem = 2 * kStageBytes + kSurvivorCap * 2 + 2 * kOutCap * 2;
+constexpr int kScanWarpSmem = 512 + kSurvivorCap * 2 + 2 * kOutCap * 2;
 constexpr uint32_t kK15 = 0x7fff7fffu;
-static_assert(kTileSamples == 32 * kStripSamples, "tile = 32 strips");
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
+static_assert(kTileSamples == 4096, "tile = 16 rows of 32 chunks");
 
 // Two I/Q pairs -> two clamped squared magnitudes, packed (low half = first sample).
 __device__ __forceinline__ uint32_t n2_pack15(uint32_t raw) {
@@ -119,35 +109,23 @@ __device__ __forceinline__ uint32_t n2_pack15(uint32_t raw) {
     return __vminu2(n0 + ((nt - n0) << 16), kK15);
 }
 
-// Queue the copy of tile g (raw I/Q of virtual chunks [512g, 512g+515)) into a stage.
-__device__ __forceinline__ void stage_tile(const BatchView &in, uint32_t stage_addr, uint32_t g, uint64_t n_vchunks,
-                                           int lane) {
-    const uint64_t c0 = (uint64_t)g * kTileChunks;
-    if (c0 >= kHaloSamples / 8 && c0 + kTileChunks + 3 <= n_vchunks) {
-        // interior tile: one base pointer, constant strides (chunk x = 32i+lane -> strip 2i+(lane>>4), slot lane&15)
-        const uint8_t *src = in.body + 16 * (c0 - kHaloSamples / 8) + 16 * lane;
-        const uint32_t dst = stage_addr + ((lane >> 4) * kStripPitch16 + (lane & 15)) * 16;
-#pragma unroll
-        for (int i = 0; i < 16; i++) cp_async16(dst + i * (2 * kStripPitch16 * 16), src + 512 * i, 16u);
-        if (lane < 3) cp_async16(stage_addr + (32 * kStripPitch16 + lane) * 16, src + 512 * 16, 16u);
-    } else {
-        // first tile (carry block) and last tile (end of the batch)
-        for (int i = 0; i < 17; i++) {
-            const int x = 32 * i + lane;                 // chunk index inside the tile, 0..514
-            if (x >= kTileChunks + 3) break;
-            const uint64_t c = c0 + x;
-            const uint8_t *src = (c < kHaloSamples / 8) ? in.halo + 16 * c : in.body + 16 * (c - kHaloSamples / 8);
-            const bool ok = c < n_vchunks;
-            cp_async16(stage_addr + ((x >> 4) * kStripPitch16 + (x & 15)) * 16, ok ? src : in.halo, ok ? 16u : 0u);
-        }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+// Where a tile's samples live: interior tiles (the common case) are one flat run of the
+// body; the first tile starts in the carry block and the last one ends the batch.
+struct TileSrc {
+    const uint8_t *flat;         // address of tile sample 0 when the tile (+24 lookahead samples) is interior
+    uint64_t c0;                 // first virtual chunk of the tile
+    bool interior;
+};
+
+__device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
+    if (t.interior) return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+    return load_vchunk(in, t.c0 + chunk, n_vchunks);
 }
 
-// Squared magnitude of the sample `d` positions after the one at `p0` (staged raw bytes);
-// `dc` = number of samples left in p0's strip (the next strip starts 16 pad bytes later).
-__device__ __forceinline__ uint32_t staged_n(const uint8_t *p0, int d, int dc) {
-    const uint32_t w = *reinterpret_cast<const uint16_t *>(p0 + 2 * d + (d >= dc ? 16 : 0));
+// Squared magnitude of tile sample s (0 .. 4096+23).
+__device__ __forceinline__ uint32_t tile_n(const BatchView &in, const TileSrc &t, int s) {
+    if (!t.interior) return sample_n(in, t.c0 * 8 + s);
+    const uint32_t w = __ldg(reinterpret_cast<const uint16_t *>(t.flat) + s);
     const uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
     return __dp4a(a, a, 0u);
 }
@@ -156,33 +134,28 @@ __device__ __forceinline__ uint32_t staged_n(const uint8_t *p0, int d, int dc) {
 //   high = (m0+m2+m7+m9)/6;  m4, m5, m11..m14 < high
 // <=> 6*(max(m4,m5,m11..m14)+1) <= m0+m2+m7+m9, and the magnitude table is monotone in the
 // squared magnitude, so the max is taken before the lookup: five lookups instead of ten.
-__device__ __forceinline__ bool high_tests(const uint8_t *stage, int s, const uint16_t *__restrict__ lutn) {
-    const int o = s & 127, dc = 128 - o;
-    const uint8_t *p0 = stage + (s >> 7) * (kStripPitch16 * 16) + 2 * o;
-    const uint32_t n0 = staged_n(p0, 0, dc), n2 = staged_n(p0, 2, dc), n7 = staged_n(p0, 7, dc), n9 = staged_n(p0, 9, dc);
-    const uint32_t n4 = staged_n(p0, 4, dc), n5 = staged_n(p0, 5, dc), n11 = staged_n(p0, 11, dc);
-    const uint32_t n12 = staged_n(p0, 12, dc), n13 = staged_n(p0, 13, dc), n14 = staged_n(p0, 14, dc);
+__device__ __forceinline__ bool high_tests(const BatchView &in, const TileSrc &t, int s, const uint16_t *__restrict__ lutn) {
+    const uint32_t n0 = tile_n(in, t, s), n2 = tile_n(in, t, s + 2), n7 = tile_n(in, t, s + 7), n9 = tile_n(in, t, s + 9);
+    const uint32_t n4 = tile_n(in, t, s + 4), n5 = tile_n(in, t, s + 5), n11 = tile_n(in, t, s + 11);
+    const uint32_t n12 = tile_n(in, t, s + 12), n13 = tile_n(in, t, s + 13), n14 = tile_n(in, t, s + 14);
     const uint32_t nx = max(max(max(n4, n5), max(n11, n12)), max(n13, n14));
     const int sum = (int)__ldg(lutn + n0) + (int)__ldg(lutn + n2) + (int)__ldg(lutn + n7) + (int)__ldg(lutn + n9);
     const int mx = __ldg(lutn + nx);
     return 6 * (mx + 1) <= sum;
 }
 
-// One lane's survivors (bits of acc[4], bit i of word g = strip position 32g+i) -> the slots
-// [excl, excl+cnt) of the tile-ordered survivor sequence; writes those that fall in
+// One lane's survivors (bits of acc[4], bit i of word g = tile position 128*lane+32g+i) -> the
+// slots [excl, excl+cnt) of the tile-ordered survivor sequence; writes those that fall in
 // [round, round+kSurvivorCap) to the list.
 __device__ __forceinline__ void list_survivors(const uint32_t acc[4], uint32_t excl, uint32_t round, uint16_t *surv,
                                                int lane) {
-    uint32_t slot = excl;
-    uint64_t w01 = acc[0] | ((uint64_t)acc[1] << 32), w23 = acc[2] | ((uint64_t)acc[3] << 32);
-    while (w01) {
-        if (slot - round < (uint32_t)kSurvivorCap) surv[slot - round] = (uint16_t)(128 * lane + __ffsll((long long)w01) - 1);
-        slot++; w01 &= w01 - 1;
-    }
-    while (w23) {
-        if (slot - round < (uint32_t)kSurvivorCap) surv[slot - round] = (uint16_t)(128 * lane + 64 + __ffsll((long long)w23) - 1);
-        slot++; w23 &= w23 - 1;
-    }
+    uint32_t slot = excl - round;
+#pragma unroll
+    for (int gq = 0; gq < 4; gq++)
+        for (uint32_t r = acc[gq]; r; r &= r - 1) {
+            if (slot < (uint32_t)kSurvivorCap) surv[slot] = (uint16_t)(128 * lane + 32 * gq + __ffs(r) - 1);
+            slot++;
+        }
 }
 
 // Copy a finished tile's candidate list (tile-local positions, position order) to its slot in the
@@ -207,82 +180,83 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes);                       // survivor positions
-    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + 2 * kStageBytes + kSurvivorCap * 2);  // 2 x candidate lists
+    uint8_t *rowmask = smem;                                                         // 512 flag bytes: byte = position/8
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 512);                       // survivor positions
+    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + 512 + kSurvivorCap * 2);  // 2 x candidate lists
     uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
 
     const int lane = threadIdx.x;
     const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
     const uint64_t t_end = in.n_samples;
 
-    uint32_t g = blockIdx.x;
-    if (g >= n_tiles) return;
-    stage_tile(in, smem_u32(smem), g, n_vchunks, lane);
-
-    for (int it = 0; g < n_tiles; g += gridDim.x, ++it) {
+    int it = 0;
+    for (uint32_t g = blockIdx.x; g < n_tiles; g += gridDim.x, ++it) {
         const int cur = it & 1;
-        if (g + gridDim.x < n_tiles) {
-            stage_tile(in, smem_u32(smem) + (cur ^ 1) * kStageBytes, g + gridDim.x, n_vchunks, lane);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        TileSrc ts;
+        ts.c0 = (uint64_t)g * kTileChunks;
+        ts.interior = ts.c0 >= kHaloSamples / 8 && ts.c0 + kTileChunks + 3 <= n_vchunks;
+        ts.flat = in.body + 16 * (ts.c0 - kHaloSamples / 8);
+
+        // ---- 16 rows of 32 chunks; three rows of loads in flight
+        uint32_t Pc[4];
+        {
+            const uint4 q0 = load_row_chunk(in, ts, lane, n_vchunks);
+            Pc[0] = n2_pack15(q0.x); Pc[1] = n2_pack15(q0.y); Pc[2] = n2_pack15(q0.z); Pc[3] = n2_pack15(q0.w);
+        }
+        uint4 q1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
+        uint4 q2 = load_row_chunk(in, ts, 64 + lane, n_vchunks);
+#pragma unroll 4
+        for (int r = 0; r < 16; r++) {
+            // row r+3 (the row after the tile only feeds the lookahead of lanes 30/31: lanes 0..2 suffice)
+            uint4 q3 = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+            if (r + 3 < 16 || (r + 3 == 16 && lane < 3)) q3 = load_row_chunk(in, ts, 32 * (r + 3) + lane, n_vchunks);
+            uint32_t Pn[4];
+            Pn[0] = n2_pack15(q1.x); Pn[1] = n2_pack15(q1.y); Pn[2] = n2_pack15(q1.z); Pn[3] = n2_pack15(q1.w);
+
+            // window of 9 packed words: own chunk, the next lane's chunk, first word of the one after
+            uint32_t P[9];
+            P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                P[4 + k] = __shfl_sync(0xffffffffu, lane == 0 ? Pn[k] : Pc[k], (lane + 1) & 31);
+            P[8] = __shfl_sync(0xffffffffu, lane < 2 ? Pn[0] : Pc[0], (lane + 2) & 31);
+
+            uint32_t T[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                // packed word u = positions 2u, 2u+1 of this chunk
+                const uint32_t S0 = __byte_perm(P[u], P[u + 1], 0x5432), S1 = __byte_perm(P[u + 1], P[u + 2], 0x5432);
+                const uint32_t S2 = __byte_perm(P[u + 2], P[u + 3], 0x5432);
+                const uint32_t S3 = __byte_perm(P[u + 3], P[u + 4], 0x5432), S4 = __byte_perm(P[u + 4], P[u + 5], 0x5432);
+                const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
+                const uint32_t cP2 = kK15 - P[u + 2], cP3 = kK15 - P[u + 3], cP4 = kK15 - P[u + 4];
+                const uint32_t A = __vminu2(P[u], P[u + 1]);                   // min(m0, m2)
+                const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
+                const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
+                const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
+                const uint32_t D1 = A + cB, D2 = P[u] + cW, D3 = S4 + cE, D4 = S3 + cP4;
+                T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2u / 2u+1 passes
+            }
+            // the 8 pass flags of this chunk as one byte, bit p = position p: PRMT lines the flag
+            // bytes up in position order, a multiply gathers bit 7 of each byte
+            const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
+            const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
+            const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
+            rowmask[32 * r + lane] = (uint8_t)(lo4 | (hi4 & 0xf0u));
+
+            Pc[0] = Pn[0]; Pc[1] = Pn[1]; Pc[2] = Pn[2]; Pc[3] = Pn[3];
+            q1 = q2; q2 = q3;
         }
         __syncwarp();
-
-        // ---- scan this lane's strip: 4 x (4 chunks of 8 positions), rolling window of packed words
-        const uint8_t *st = smem + cur * kStageBytes;
-        const uint4 *sp = reinterpret_cast<const uint4 *>(st) + lane * kStripPitch16;
-        uint32_t P[24];                                  // chunks 4q .. 4q+5 of the strip
+        // lane j now takes the 128 consecutive positions [128j, 128j+128) of the tile
+        uint32_t acc[4];
         {
-            uint4 r0 = sp[0], r1 = sp[1];
-            P[0] = n2_pack15(r0.x); P[1] = n2_pack15(r0.y); P[2] = n2_pack15(r0.z); P[3] = n2_pack15(r0.w);
-            P[4] = n2_pack15(r1.x); P[5] = n2_pack15(r1.y); P[6] = n2_pack15(r1.z); P[7] = n2_pack15(r1.w);
-        }
-        uint32_t acc[4] = {0u, 0u, 0u, 0u};
-#pragma unroll 1
-        for (int q = 0; q < 4; q++) {
-            // squared magnitudes of chunks 4q+2 .. 4q+5 (chunks 16,17 are the next strip's first two)
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int cc = 4 * q + 2 + k;
-                const uint4 r = sp[cc + (cc >= 16 ? 1 : 0)];
-                P[8 + 4 * k + 0] = n2_pack15(r.x); P[8 + 4 * k + 1] = n2_pack15(r.y);
-                P[8 + 4 * k + 2] = n2_pack15(r.z); P[8 + 4 * k + 3] = n2_pack15(r.w);
-            }
-            uint32_t word = 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                uint32_t T[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const int w = 4 * c + u;             // packed word = positions 2w, 2w+1 of this group
-                    // odd-aligned pairs S[x] = (n[2x+1], n[2x+2]) and complements
-                    const uint32_t S0 = __byte_perm(P[w], P[w + 1], 0x5432), S1 = __byte_perm(P[w + 1], P[w + 2], 0x5432);
-                    const uint32_t S2 = __byte_perm(P[w + 2], P[w + 3], 0x5432);
-                    const uint32_t S3 = __byte_perm(P[w + 3], P[w + 4], 0x5432), S4 = __byte_perm(P[w + 4], P[w + 5], 0x5432);
-                    const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
-                    const uint32_t cP2 = kK15 - P[w + 2], cP3 = kK15 - P[w + 3], cP4 = kK15 - P[w + 4];
-                    const uint32_t A = __vminu2(P[w], P[w + 1]);                   // min(m0, m2)
-                    const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
-                    const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
-                    const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
-                    const uint32_t D1 = A + cB, D2 = P[w] + cW, D3 = S4 + cE, D4 = S3 + cP4;
-                    T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2w / 2w+1 passes
-                }
-                // the 8 pass flags of this chunk as one byte, bit p = position 8c+p: PRMT lines the
-                // flag bytes up in position order, a multiply gathers bit 7 of each byte
-                const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
-                const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
-                const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
-                word |= (lo4 | (hi4 & 0xf0u)) << (8 * c);
-            }
-            acc[0] = acc[1]; acc[1] = acc[2]; acc[2] = acc[3]; acc[3] = word;       // after 4 rounds: acc[q] = group q
-#pragma unroll
-            for (int k = 0; k < 8; k++) P[k] = P[16 + k];                           // slide the window by 4 chunks
+            const uint4 m4 = reinterpret_cast<const uint4 *>(rowmask)[lane];
+            acc[0] = m4.x; acc[1] = m4.y; acc[2] = m4.z; acc[3] = m4.w;
         }
 
         // ---- write out the PREVIOUS tile's candidates: its slot in the global array (one atomic
-        // per tile) was claimed before this tile's strip scan, so the round trip is hidden
+        // per tile) was claimed before this tile's rows were scanned, so the round trip is hidden
         if (pend_tile != 0xffffffffu) {
             emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
             pend_tile = 0xffffffffu;
@@ -321,7 +295,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             for (uint32_t i0 = 0; i0 < n_surv; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const int spos = i < n_surv ? surv[i] : 0;
-                const bool pass = i < n_surv && high_tests(st, spos, lutn);
+                const bool pass = i < n_surv && high_tests(in, ts, spos, lutn);
                 const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                 const uint32_t slot = n_out + __popc(bal & ((1u << lane) - 1u));
                 if (pass && slot < (uint32_t)kOutCap) olist[slot] = (uint16_t)spos;
@@ -351,7 +325,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                     for (uint32_t i0 = 0; i0 < n_here; i0 += 32) {
                         const uint32_t i = i0 + lane;
                         const int spos = i < n_here ? surv[i] : 0;
-                        const bool pass = i < n_here && high_tests(st, spos, lutn);
+                        const bool pass = i < n_here && high_tests(in, ts, spos, lutn);
                         const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                         if (pass_no == 1 && pass) {
                             const uint32_t idx = base + run + __popc(bal & ((1u << lane) - 1u));
@@ -372,7 +346,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                 }
             }
         }
-        __syncwarp();                                    // this stage and the lists are reused later
+        __syncwarp();                                    // rowmask and the lists are reused by the next tile
     }
     if (pend_tile != 0xffffffffu) emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
 }
@@ -385,7 +359,7 @@ void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs
         attr_set = true;
     }
     const uint32_t n_tiles = tiles_for(in.n_samples);
-    uint32_t grid = (uint32_t)sm_count * 11;             // 11 single-warp CTAs fit one SM's shared memory
+    uint32_t grid = (uint32_t)sm_count * 32;             // 32 single-warp CTAs per SM (the CTA-per-SM limit)
     if (grid > n_tiles) grid = n_tiles;
     scan_kernel<<<grid, 32, kScanWarpSmem, stream>>>(in, tab.lutn, out, n_tiles);
 }
