@@ -97,7 +97,8 @@ __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
 constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
 constexpr int kSurvivorCap = 512;
 constexpr int kOutCap = 256;                             // candidates per tile held back one tile
-constexpr int kScanWarpSmem = 512 + kSurvivorCap * 2 + 2 * kOutCap * 2;
+constexpr int kRawBytes = kTileSamples * 2 + 512;         // the tile's raw I/Q + the row after it, kept for the exact tests
+constexpr int kScanWarpSmem = kRawBytes + 512 + kSurvivorCap * 2 + 2 * kOutCap * 2;
 constexpr uint32_t kK15 = 0x7fff7fffu;
 static_assert(kTileSamples == 4096, "tile = 16 rows of 32 chunks");
 
@@ -122,10 +123,9 @@ __device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileS
     return load_vchunk(in, t.c0 + chunk, n_vchunks);
 }
 
-// Squared magnitude of tile sample s (0 .. 4096+23).
-__device__ __forceinline__ uint32_t tile_n(const BatchView &in, const TileSrc &t, int s) {
-    if (!t.interior) return sample_n(in, t.c0 * 8 + s);
-    const uint32_t w = __ldg(reinterpret_cast<const uint16_t *>(t.flat) + s);
+// Squared magnitude of tile sample s (0 .. 4096+23) from the warp's shared-memory copy.
+__device__ __forceinline__ uint32_t tile_n(const uint8_t *raw, int s) {
+    const uint32_t w = *reinterpret_cast<const uint16_t *>(raw + 2 * s);
     const uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
     return __dp4a(a, a, 0u);
 }
@@ -134,10 +134,10 @@ __device__ __forceinline__ uint32_t tile_n(const BatchView &in, const TileSrc &t
 //   high = (m0+m2+m7+m9)/6;  m4, m5, m11..m14 < high
 // <=> 6*(max(m4,m5,m11..m14)+1) <= m0+m2+m7+m9, and the magnitude table is monotone in the
 // squared magnitude, so the max is taken before the lookup: five lookups instead of ten.
-__device__ __forceinline__ bool high_tests(const BatchView &in, const TileSrc &t, int s, const uint16_t *__restrict__ lutn) {
-    const uint32_t n0 = tile_n(in, t, s), n2 = tile_n(in, t, s + 2), n7 = tile_n(in, t, s + 7), n9 = tile_n(in, t, s + 9);
-    const uint32_t n4 = tile_n(in, t, s + 4), n5 = tile_n(in, t, s + 5), n11 = tile_n(in, t, s + 11);
-    const uint32_t n12 = tile_n(in, t, s + 12), n13 = tile_n(in, t, s + 13), n14 = tile_n(in, t, s + 14);
+__device__ __forceinline__ bool high_tests(const uint8_t *raw, int s, const uint16_t *__restrict__ lutn) {
+    const uint32_t n0 = tile_n(raw, s), n2 = tile_n(raw, s + 2), n7 = tile_n(raw, s + 7), n9 = tile_n(raw, s + 9);
+    const uint32_t n4 = tile_n(raw, s + 4), n5 = tile_n(raw, s + 5), n11 = tile_n(raw, s + 11);
+    const uint32_t n12 = tile_n(raw, s + 12), n13 = tile_n(raw, s + 13), n14 = tile_n(raw, s + 14);
     const uint32_t nx = max(max(max(n4, n5), max(n11, n12)), max(n13, n14));
     const int sum = (int)__ldg(lutn + n0) + (int)__ldg(lutn + n2) + (int)__ldg(lutn + n7) + (int)__ldg(lutn + n9);
     const int mx = __ldg(lutn + nx);
@@ -177,75 +177,93 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
     }
 }
 
+// One row of the tile: positions 256r+8*lane .. +7.  `Pc` = this lane's packed squared
+// magnitudes for row r, `xn` = raw chunk of row r+1 (becomes Pc; kept in shared memory for the
+// exact tests), then refilled with row r+5.
+#define MODES_SCAN_ROW(r_, xn)                                                                                     \
+    {                                                                                                              \
+        const int r = (r_);                                                                                        \
+        uint32_t Pn[4];                                                                                            \
+        Pn[0] = n2_pack15(xn.x); Pn[1] = n2_pack15(xn.y); Pn[2] = n2_pack15(xn.z); Pn[3] = n2_pack15(xn.w);        \
+        reinterpret_cast<uint4 *>(raw)[32 * (r + 1) + lane] = xn;                                                  \
+        if (r + 5 < 16 || (r + 5 == 16 && lane < 3)) xn = load_row_chunk(in, ts, 32 * (r + 5) + lane, n_vchunks);  \
+        uint32_t P[9];                                                                                             \
+        P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];                                                    \
+        _Pragma("unroll") for (int k = 0; k < 4; k++)                                                              \
+            P[4 + k] = __shfl_sync(0xffffffffu, lane == 0 ? Pn[k] : Pc[k], (lane + 1) & 31);                       \
+        P[8] = __shfl_sync(0xffffffffu, lane < 2 ? Pn[0] : Pc[0], (lane + 2) & 31);                                \
+        uint32_t T[4];                                                                                             \
+        _Pragma("unroll") for (int u = 0; u < 4; u++) {                                                            \
+            const uint32_t S0 = __byte_perm(P[u], P[u + 1], 0x5432), S1 = __byte_perm(P[u + 1], P[u + 2], 0x5432); \
+            const uint32_t S2 = __byte_perm(P[u + 2], P[u + 3], 0x5432);                                           \
+            const uint32_t S3 = __byte_perm(P[u + 3], P[u + 4], 0x5432), S4 = __byte_perm(P[u + 4], P[u + 5], 0x5432); \
+            const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;                                      \
+            const uint32_t cP2 = kK15 - P[u + 2], cP3 = kK15 - P[u + 3], cP4 = kK15 - P[u + 4];                    \
+            const uint32_t A = __vminu2(P[u], P[u + 1]);        /* min(m0, m2)          */                         \
+            const uint32_t cB = __vminu2(cS0, cS1);             /* K - max(m1, m3)      */                         \
+            const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);  /* K - max(m4, m5, m6)  */                         \
+            const uint32_t cE = __vminu2(cP3, cP4);             /* K - max(m6, m8)      */                         \
+            const uint32_t D1 = A + cB, D2 = P[u] + cW, D3 = S4 + cE, D4 = S3 + cP4;                               \
+            T[u] = D1 & D2 & D3 & D4;                           /* bit 15 / 31: position 2u / 2u+1 passes */       \
+        }                                                                                                          \
+        const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);                   \
+        const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;                                              \
+        const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;                                              \
+        rowmask[32 * r + lane] = (uint8_t)(lo4 | (hi4 & 0xf0u));                                                   \
+        Pc[0] = Pn[0]; Pc[1] = Pn[1]; Pc[2] = Pn[2]; Pc[3] = Pn[3];                                                \
+    }
+
+__device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, uint64_t n_vchunks) {
+    TileSrc ts;
+    ts.c0 = (uint64_t)g * kTileChunks;
+    ts.interior = ts.c0 >= kHaloSamples / 8 && ts.c0 + kTileChunks + 3 <= n_vchunks;
+    ts.flat = in.body + 16 * (ts.c0 - kHaloSamples / 8);
+    return ts;
+}
+
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *rowmask = smem;                                                         // 512 flag bytes: byte = position/8
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + 512);                       // survivor positions
-    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + 512 + kSurvivorCap * 2);  // 2 x candidate lists
+    uint8_t *raw = smem;                                                             // tile's raw I/Q (17 rows), chunk order
+    uint8_t *rowmask = smem + kRawBytes;                                             // 512 flag bytes: byte = position/8
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + kRawBytes + 512);           // survivor positions
+    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + kRawBytes + 512 + kSurvivorCap * 2);  // 2 x candidate lists
     uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
 
     const int lane = threadIdx.x;
     const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
     const uint64_t t_end = in.n_samples;
 
-    int it = 0;
-    for (uint32_t g = blockIdx.x; g < n_tiles; g += gridDim.x, ++it) {
+    // rows 0..3 of the first tile
+    uint32_t g = blockIdx.x;
+    if (g >= n_tiles) return;
+    TileSrc ts = tile_source(in, g, n_vchunks);
+    uint4 x0 = load_row_chunk(in, ts, lane, n_vchunks), x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
+    uint4 x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
+
+    for (int it = 0; g < n_tiles; ++it) {
         const int cur = it & 1;
-        TileSrc ts;
-        ts.c0 = (uint64_t)g * kTileChunks;
-        ts.interior = ts.c0 >= kHaloSamples / 8 && ts.c0 + kTileChunks + 3 <= n_vchunks;
-        ts.flat = in.body + 16 * (ts.c0 - kHaloSamples / 8);
 
-        // ---- 16 rows of 32 chunks; three rows of loads in flight
+        // ---- 16 rows of 32 chunks, four rows of loads in flight.  Ring: x1 = row 1, x2 = row 2,
+        // x3 = row 3, x0 = row 4 (once row 0 has been consumed)
         uint32_t Pc[4];
-        {
-            const uint4 q0 = load_row_chunk(in, ts, lane, n_vchunks);
-            Pc[0] = n2_pack15(q0.x); Pc[1] = n2_pack15(q0.y); Pc[2] = n2_pack15(q0.z); Pc[3] = n2_pack15(q0.w);
+        Pc[0] = n2_pack15(x0.x); Pc[1] = n2_pack15(x0.y); Pc[2] = n2_pack15(x0.z); Pc[3] = n2_pack15(x0.w);
+        reinterpret_cast<uint4 *>(raw)[lane] = x0;
+        x0 = load_row_chunk(in, ts, 128 + lane, n_vchunks);
+#pragma unroll 1
+        for (int rr = 0; rr < 16; rr += 4) {
+            MODES_SCAN_ROW(rr + 0, x1)
+            MODES_SCAN_ROW(rr + 1, x2)
+            MODES_SCAN_ROW(rr + 2, x3)
+            MODES_SCAN_ROW(rr + 3, x0)
         }
-        uint4 q1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
-        uint4 q2 = load_row_chunk(in, ts, 64 + lane, n_vchunks);
-#pragma unroll 4
-        for (int r = 0; r < 16; r++) {
-            // row r+3 (the row after the tile only feeds the lookahead of lanes 30/31: lanes 0..2 suffice)
-            uint4 q3 = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-            if (r + 3 < 16 || (r + 3 == 16 && lane < 3)) q3 = load_row_chunk(in, ts, 32 * (r + 3) + lane, n_vchunks);
-            uint32_t Pn[4];
-            Pn[0] = n2_pack15(q1.x); Pn[1] = n2_pack15(q1.y); Pn[2] = n2_pack15(q1.z); Pn[3] = n2_pack15(q1.w);
 
-            // window of 9 packed words: own chunk, the next lane's chunk, first word of the one after
-            uint32_t P[9];
-            P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                P[4 + k] = __shfl_sync(0xffffffffu, lane == 0 ? Pn[k] : Pc[k], (lane + 1) & 31);
-            P[8] = __shfl_sync(0xffffffffu, lane < 2 ? Pn[0] : Pc[0], (lane + 2) & 31);
-
-            uint32_t T[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                // packed word u = positions 2u, 2u+1 of this chunk
-                const uint32_t S0 = __byte_perm(P[u], P[u + 1], 0x5432), S1 = __byte_perm(P[u + 1], P[u + 2], 0x5432);
-                const uint32_t S2 = __byte_perm(P[u + 2], P[u + 3], 0x5432);
-                const uint32_t S3 = __byte_perm(P[u + 3], P[u + 4], 0x5432), S4 = __byte_perm(P[u + 4], P[u + 5], 0x5432);
-                const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;
-                const uint32_t cP2 = kK15 - P[u + 2], cP3 = kK15 - P[u + 3], cP4 = kK15 - P[u + 4];
-                const uint32_t A = __vminu2(P[u], P[u + 1]);                   // min(m0, m2)
-                const uint32_t cB = __vminu2(cS0, cS1);                        // K - max(m1, m3)
-                const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);             // K - max(m4, m5, m6)
-                const uint32_t cE = __vminu2(cP3, cP4);                        // K - max(m6, m8)
-                const uint32_t D1 = A + cB, D2 = P[u] + cW, D3 = S4 + cE, D4 = S3 + cP4;
-                T[u] = D1 & D2 & D3 & D4;                                      // bit 15 / 31: position 2u / 2u+1 passes
-            }
-            // the 8 pass flags of this chunk as one byte, bit p = position p: PRMT lines the flag
-            // bytes up in position order, a multiply gathers bit 7 of each byte
-            const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);
-            const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;
-            const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;
-            rowmask[32 * r + lane] = (uint8_t)(lo4 | (hi4 & 0xf0u));
-
-            Pc[0] = Pn[0]; Pc[1] = Pn[1]; Pc[2] = Pn[2]; Pc[3] = Pn[3];
-            q1 = q2; q2 = q3;
+        // ---- start the next tile's first four rows now; they arrive while this tile is finished
+        const uint32_t g_next = g + gridDim.x;
+        if (g_next < n_tiles) {
+            ts = tile_source(in, g_next, n_vchunks);
+            x0 = load_row_chunk(in, ts, lane, n_vchunks); x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
+            x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks); x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
         }
         __syncwarp();
         // lane j now takes the 128 consecutive positions [128j, 128j+128) of the tile
@@ -295,7 +313,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             for (uint32_t i0 = 0; i0 < n_surv; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const int spos = i < n_surv ? surv[i] : 0;
-                const bool pass = i < n_surv && high_tests(in, ts, spos, lutn);
+                const bool pass = i < n_surv && high_tests(raw, spos, lutn);
                 const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                 const uint32_t slot = n_out + __popc(bal & ((1u << lane) - 1u));
                 if (pass && slot < (uint32_t)kOutCap) olist[slot] = (uint16_t)spos;
@@ -325,7 +343,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                     for (uint32_t i0 = 0; i0 < n_here; i0 += 32) {
                         const uint32_t i = i0 + lane;
                         const int spos = i < n_here ? surv[i] : 0;
-                        const bool pass = i < n_here && high_tests(in, ts, spos, lutn);
+                        const bool pass = i < n_here && high_tests(raw, spos, lutn);
                         const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                         if (pass_no == 1 && pass) {
                             const uint32_t idx = base + run + __popc(bal & ((1u << lane) - 1u));
@@ -346,20 +364,23 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                 }
             }
         }
-        __syncwarp();                                    // rowmask and the lists are reused by the next tile
+        __syncwarp();                                    // raw, rowmask and the lists are reused by the next tile
+        g = g_next;
     }
     if (pend_tile != 0xffffffffu) emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
 }
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
         cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanWarpSmem);
-        attr_set = true;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel, 32, kScanWarpSmem) != cudaSuccess ||
+            ctas_per_sm < 1)
+            ctas_per_sm = 16;
     }
     const uint32_t n_tiles = tiles_for(in.n_samples);
-    uint32_t grid = (uint32_t)sm_count * 32;             // 32 single-warp CTAs per SM (the CTA-per-SM limit)
+    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);  // persistent single-warp CTAs, all resident
     if (grid > n_tiles) grid = n_tiles;
     scan_kernel<<<grid, 32, kScanWarpSmem, stream>>>(in, tab.lutn, out, n_tiles);
 }
