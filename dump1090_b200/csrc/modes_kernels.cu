@@ -179,14 +179,13 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
 
 // One row of the tile: positions 256r+8*lane .. +7.  `Pc` = this lane's packed squared
 // magnitudes for row r, `xn` = raw chunk of row r+1 (becomes Pc; kept in shared memory for the
-// exact tests), then refilled with row r+5.
+// exact tests).
 #define MODES_SCAN_ROW(r_, xn)                                                                                     \
     {                                                                                                              \
         const int r = (r_);                                                                                        \
         uint32_t Pn[4];                                                                                            \
         Pn[0] = n2_pack15(xn.x); Pn[1] = n2_pack15(xn.y); Pn[2] = n2_pack15(xn.z); Pn[3] = n2_pack15(xn.w);        \
         reinterpret_cast<uint4 *>(raw)[32 * (r + 1) + lane] = xn;                                                  \
-        if (r + 5 < 16 || (r + 5 == 16 && lane < 3)) xn = load_row_chunk(in, ts, 32 * (r + 5) + lane, n_vchunks);  \
         uint32_t P[9];                                                                                             \
         P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];                                                    \
         _Pragma("unroll") for (int k = 0; k < 4; k++)                                                              \
@@ -244,18 +243,29 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
     for (int it = 0; g < n_tiles; ++it) {
         const int cur = it & 1;
 
-        // ---- 16 rows of 32 chunks, four rows of loads in flight.  Ring: x1 = row 1, x2 = row 2,
-        // x3 = row 3, x0 = row 4 (once row 0 has been consumed)
+        // ---- 16 rows of 32 chunks.  x0..x3 hold rows 4k..4k+3 on entry of group k; the four loads
+        // of the next group are issued together at the top of the group (one scoreboard group,
+        // a full group of arithmetic between issue and first use).
         uint32_t Pc[4];
         Pc[0] = n2_pack15(x0.x); Pc[1] = n2_pack15(x0.y); Pc[2] = n2_pack15(x0.z); Pc[3] = n2_pack15(x0.w);
         reinterpret_cast<uint4 *>(raw)[lane] = x0;
-        x0 = load_row_chunk(in, ts, 128 + lane, n_vchunks);
 #pragma unroll 1
         for (int rr = 0; rr < 16; rr += 4) {
+            const uint4 pad = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
+            uint4 y0 = pad, y1 = pad, y2 = pad, y3 = pad;       // rows rr+4 .. rr+7
+            if (rr + 4 < 16) {
+                y0 = load_row_chunk(in, ts, 32 * (rr + 4) + lane, n_vchunks);
+                y1 = load_row_chunk(in, ts, 32 * (rr + 5) + lane, n_vchunks);
+                y2 = load_row_chunk(in, ts, 32 * (rr + 6) + lane, n_vchunks);
+                y3 = load_row_chunk(in, ts, 32 * (rr + 7) + lane, n_vchunks);
+            } else if (lane < 3) {
+                y0 = load_row_chunk(in, ts, 32 * 16 + lane, n_vchunks);   // the row after the tile: lookahead only
+            }
             MODES_SCAN_ROW(rr + 0, x1)
             MODES_SCAN_ROW(rr + 1, x2)
             MODES_SCAN_ROW(rr + 2, x3)
-            MODES_SCAN_ROW(rr + 3, x0)
+            MODES_SCAN_ROW(rr + 3, y0)
+            x1 = y1; x2 = y2; x3 = y3;
         }
 
         // ---- start the next tile's first four rows now; they arrive while this tile is finished
