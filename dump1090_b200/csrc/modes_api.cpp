@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <string>
 #include <vector>
@@ -212,18 +213,29 @@ int wait_batch(modes_ctx *ctx, Slot &s, uint64_t *n_out) {
 }
 
 // Fetch the slot's results to pinned host memory and run the sequential resolve.
+double now_ms() {
+    timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec * 1e3 + t.tv_nsec * 1e-6;
+}
+
 int collect(modes_ctx *ctx, Slot &s) {
     if (!s.busy) return 0;
     s.busy = false;
     uint64_t n = 0;
+    static const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
+    const double t0 = dbg ? now_ms() : 0;
     if (wait_batch(ctx, s, &n)) return -1;
+    const double t1 = dbg ? now_ms() : 0;
     const size_t nt = tiles_for((uint64_t)s.n_buffers * kBufSamples);
     if (host_ensure(ctx, s, n, nt)) return -1;
     if (n) CK(ctx, cudaMemcpyAsync(s.h_records, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaMemcpyAsync(s.h_tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaStreamSynchronize(s.stream));
+    const double t2 = dbg ? now_ms() : 0;
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
     resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->out);
+    if (dbg) fprintf(stderr, "[collect] %zu buffers, %llu cands: wait %.3f ms, d2h %.3f ms, resolve %.3f ms (t=%.3f)\n",
+                     s.n_buffers, (unsigned long long)n, t1 - t0, t2 - t1, now_ms() - t2, now_ms());
     return 0;
 }
 
@@ -266,7 +278,7 @@ void modes_default_config(modes_config *cfg) {
     cfg->drop_eof_buffer = 0;
     cfg->device = 0;
     cfg->profile = 0;
-    cfg->max_batch_bytes = 256ull << 20;
+    cfg->max_batch_bytes = 64ull << 20;
 }
 
 const char *modes_last_error(const modes_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -317,7 +329,7 @@ modes_ctx *modes_create(const modes_config *cfg) {
     modes_ctx *ctx = new (std::nothrow) modes_ctx();
     if (!ctx) { g_create_error = "out of memory"; return nullptr; }
     if (cfg) ctx->cfg = *cfg; else modes_default_config(&ctx->cfg);
-    if (ctx->cfg.max_batch_bytes == 0) ctx->cfg.max_batch_bytes = 256ull << 20;
+    if (ctx->cfg.max_batch_bytes == 0) ctx->cfg.max_batch_bytes = 64ull << 20;
     ctx->rs.reset();
     memset(ctx->carry, 127, sizeof(ctx->carry));
     if (create_impl(ctx)) { modes_destroy(ctx); return nullptr; }

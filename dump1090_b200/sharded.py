@@ -73,6 +73,16 @@ def gather_records(cands, tiles, n_cand: int, dist=None, group=None, dst: int = 
 def resolve_gathered(resolver, gathered, plan) -> None:
     """Rank 0: replay the sequential half over the shards in stream order."""
     for (c, t), (first, _n) in zip(gathered, plan):
-        c_np = np.frombuffer(c.cpu().numpy().tobytes(), dtype=api.CANDIDATE_DTYPE)
-        t_np = np.frombuffer(t.cpu().numpy().tobytes(), dtype=api.TILE_DTYPE)
+        c_np = c.cpu().numpy().view(api.CANDIDATE_DTYPE) if c.numel() else np.zeros(0, dtype=api.CANDIDATE_DTYPE)
+        t_np = t.cpu().numpy().view(api.TILE_DTYPE)
         resolver.run(c_np, t_np, buffer_base=first)
+
+
+def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):
+    """Gather fixed-size record/tile buffers to rank `dst` with no host round trip (counts travel
+    in the tile tables).  `out` = preallocated ([world x cands], [world x tiles]) on dst.  Returns
+    the two async work handles."""
+    rank = dist.get_rank(group)
+    w1 = dist.gather(cands, out[0] if rank == dst else None, dst=dst, group=group, async_op=True)
+    w2 = dist.gather(tiles, out[1] if rank == dst else None, dst=dst, group=group, async_op=True)
+    return w1, w2

@@ -47,7 +47,7 @@ typedef struct modes_config {
                                    stock binary does in most runs */
     int32_t device;             /* CUDA device ordinal, default 0 */
     int32_t profile;            /* 1: record per-kernel CUDA-event times (modes_get_kernel_times) */
-    uint64_t max_batch_bytes;   /* device staging per in-flight batch; 0 = 256 MiB */
+    uint64_t max_batch_bytes;   /* device staging per in-flight batch; 0 = 64 MiB */
 } modes_config;
 
 /* Replaces struct modesMessage (dump1090.c:211-260): same field names and
