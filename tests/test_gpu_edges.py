@@ -1,0 +1,147 @@
+"""-m gpu: edge cases, the hex door, the C host binary, and full-size properties."""
+import ctypes
+import hashlib
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import checker as C
+from dump1090_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _lines(msgs):
+    return [m.raw_line() for m in msgs]
+
+
+def _olines(msgs):
+    return [m.hexline() for m in msgs]
+
+
+@pytest.mark.parametrize("nbytes", [0, 1, 2, 477, 5000, 262143, 262144, 262145, 524288, 600001])
+@pytest.mark.parametrize("drop", [0, 1])
+def test_ragged_lengths(nbytes, drop, gpu_decoder_factory, checker_libs):
+    """Empty, odd, one-short, exact-buffer and one-over inputs: same EOF-buffer semantics as the
+    reference (dump1090.c:481-507), both outcomes of its EOF race."""
+    data = synth.random_traffic(300001, 420, 17)[:nbytes]
+    exp, st = C.oracle_decode(data, drop_eof=drop)
+    dec = gpu_decoder_factory(drop_eof_buffer=drop)
+    got = dec.decode(data)
+    assert _lines(got) == _olines(exp)
+    assert list(dec.stats().values()) == st
+
+
+def test_frame_at_every_buffer_seam_offset(gpu_decoder_factory, checker_libs):
+    """A strong DF17 frame slid across the 131072-sample buffer seam: carry-over and the two
+    untested positions per buffer (j = 131070, 131071) behave as in the reference."""
+    frame = synth.make_frame(17, 5, bytes.fromhex("4840d6202cc371c32ce0"))
+    dec = gpu_decoder_factory()
+    for start in list(range(131072 - 250, 131072 - 225)) + [130830, 130831, 130832, 130833, 130834]:
+        s = synth.synth_stream(131072 + 2000, [(start, frame, 80.0, 0.7, 0.0)], sigma=1.0, seed=start)
+        exp, _ = C.oracle_decode(s)
+        assert _lines(dec.decode(s)) == _olines(exp), start
+
+
+def test_saturated_samples(gpu_decoder_factory, checker_libs):
+    """Bytes 0 and 255 (|x-127| = 127/128, squared magnitudes up to 32768) keep exact ordering."""
+    frame = synth.make_frame(17, 5, bytes.fromhex("4840d6202cc371c32ce0"))
+    s = synth.synth_stream(200000, [(1000 + 400 * k, frame, 150.0 + 10 * k, 0.1 * k, 0.3 * (k % 3)) for k in range(300)],
+                           sigma=3.0, seed=5)
+    assert s.max() == 255 and s.min() == 0
+    exp, st = C.oracle_decode(s, aggressive=1)
+    dec = gpu_decoder_factory(aggressive=1)
+    assert _lines(dec.decode(s)) == _olines(exp)
+    assert list(dec.stats().values()) == st
+    assert np.array_equal(dec.magnitude(s), C.oracle_magnitude(s))
+
+
+def test_reset_and_reuse(gpu_decoder_factory, checker_libs):
+    dec = gpu_decoder_factory()
+    a = synth.random_traffic(200000, 250, 61)
+    b = C.modes1()
+    ea, _ = C.oracle_decode(a)
+    eb, _ = C.oracle_decode(b)
+    for _ in range(2):
+        assert _lines(dec.decode(a)) == _olines(ea)
+        assert _lines(dec.decode(b)) == _olines(eb)
+
+
+def test_output_array_equals_callback(gpu_decoder_factory, checker_libs):
+    data = C.modes1()
+    dec = gpu_decoder_factory()
+    want = _lines(dec.decode(data))
+    out = dec.set_output_array(1000)
+    dec.reset(); dec.rearm_output(); dec.process(data); dec.finish()
+    n = dec.output_count()
+    assert [out[i].raw_line() for i in range(n)] == want
+    dec.set_output_array(0)
+
+
+@pytest.mark.skipif(not C.have_ref(), reason="needs oracle/_ref")
+def test_hex_door_matches_reference(gpu_decoder_factory, checker_libs):
+    """modes_decode_frame == decodeModesMessage on frame bytes (dump1090.c:2472-2502), incl. repairs."""
+    rng = synth.Counter(7)
+    ref = C.ref_lib()
+    for aggressive in (0, 1):
+        for k in range(120):
+            df = [17, 17, 18, 11, 4, 5, 20, 21, 0, 16][k % 10]
+            body = bytes(rng.below(256) for _ in range(10 if df >= 16 else 3))
+            frame = synth.flip_bits(synth.make_frame(df, rng.below(8), body), [rng.below(56) for _ in range(k % 3)])
+            frame = frame.ljust(14, b"\0")
+            dec = gpu_decoder_factory(aggressive=aggressive)      # fresh ICAO cache, like the harness
+            want = C.Msg()
+            ref.ref_decode_bytes(frame, 1, aggressive, ctypes.byref(want))
+            got = dec.decode_frame(frame)
+            assert C.msg_fields(got) == C.msg_fields(want), (k, aggressive)
+            dec.close()
+
+
+def test_c_host_binary(checker_libs):
+    """./dump1090-b200 --ifile modes1.bin --raw prints the reference's lines (SURVEY.md §4 md5 pins)."""
+    exe = ROOT / "dump1090-b200"
+    assert exe.exists(), "build the C host with `make`"
+    f = str(C.modes1_path())
+    pins = {(): (284, "4a81758c8bec"), ("--drop-eof-buffer",): (217, "7b1719f22374"),
+            ("--no-fix",): (283, "ac539444a66e"), ("--no-crc-check",): (765, "a6092d178fcf"),
+            ("--no-crc-check", "--aggressive"): (824, "bec25488d6b8")}
+    for flags, (n, md5) in pins.items():
+        out = subprocess.run([str(exe), "--ifile", f, "--raw", *flags], capture_output=True, check=True).stdout
+        assert out.count(b"\n") == n and hashlib.md5(out).hexdigest().startswith(md5), flags
+    stats = subprocess.run([str(exe), "--ifile", f, "--stats"], capture_output=True, check=True, text=True).stdout
+    assert stats.splitlines()[:4] == ["546 valid preambles", "282 demodulated again after phase correction",
+                                      "535 demodulated with zero errors", "276 with good crc"]
+
+
+def test_full_size_properties(gpu_decoder_factory, checker_libs):
+    """BASELINE.json configs[1] size (modes1.bin tiled to 1 GiB, --no-fix): prefix equality with the
+    oracle, invariance to feed chunking / batch size, determinism."""
+    data = synth.tile_to(C.modes1(), 1 << 30)
+    dec = gpu_decoder_factory(fix_errors=0)
+    out = dec.set_output_array(700000)
+    dec.reset(); dec.rearm_output(); dec.process(data); dec.finish()
+    n = dec.output_count()
+    assert n == 425744
+    pos = np.array([out[i].sample_pos for i in range(n)])
+    assert np.all(np.diff(pos) > 0), "messages must come out in stream order"
+    digest = hashlib.sha256(b"".join(bytes(out[i].msg) for i in range(n))).hexdigest()
+    stats = dec.stats()
+    # prefix: the first 256 reference buffers, checked message for message against the oracle
+    k = 256
+    exp, _ = C.oracle_decode(data[: k * api.BUFFER_BYTES], fix=0, drop_eof=1)
+    cut = int(np.searchsorted(pos, k * api.BUFFER_SAMPLES - 240))
+    assert [out[i].raw_line() for i in range(cut)] == [m.hexline() for m in exp]
+    # same stream, different chunking and batch size -> identical messages and statistics
+    dec2 = gpu_decoder_factory(fix_errors=0, max_batch_bytes=api.BUFFER_BYTES * 7)
+    out2 = dec2.set_output_array(700000)
+    dec2.reset(); dec2.rearm_output()
+    step = 100 * 1000 * 1000 + 1
+    for off in range(0, data.size, step):
+        dec2.process(data[off: off + step])
+    dec2.finish()
+    assert dec2.output_count() == n
+    assert hashlib.sha256(b"".join(bytes(out2[i].msg) for i in range(n))).hexdigest() == digest
+    assert dec2.stats() == stats
