@@ -155,6 +155,10 @@ def run_ours(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # keep stdout clean for the one JSON line (NCCL prints its version banner there)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the decode path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -353,7 +357,10 @@ def run_ours(args) -> None:
                          "batches_timed": int(ktimes[3])},
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(out), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

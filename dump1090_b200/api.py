@@ -94,7 +94,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_host_alloc",
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
 
@@ -127,6 +127,8 @@ def lib():
         L.modes_resolver_destroy.argtypes = [C.c_void_p]
         L.modes_resolver_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, SINK_FN,
                                          C.c_void_p]
+        L.modes_resolver_run_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, SINK_FN, C.c_void_p]
         L.modes_resolver_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.modes_resolver_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.modes_resolver_output_count.restype = C.c_size_t
@@ -361,6 +363,18 @@ class Resolver:
         rc = lib().modes_resolver_run(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base, fn, None)
         if rc:
             raise RuntimeError("modes_resolver_run failed")
+
+    def run_shards(self, shards) -> None:
+        """shards: [(cands ndarray, tiles ndarray, buffer_base)] in stream order; resolved concurrently."""
+        n = len(shards)
+        keep = [(np.ascontiguousarray(c), np.ascontiguousarray(t)) for c, t, _ in shards]
+        cp = (C.c_void_p * n)(*[c.ctypes.data for c, _ in keep])
+        tp = (C.c_void_p * n)(*[t.ctypes.data for _, t in keep])
+        nt = (C.c_size_t * n)(*[t.size for _, t in keep])
+        bb = (C.c_int64 * n)(*[int(b) for _, _, b in shards])
+        fn = C.cast(None, SINK_FN) if getattr(self, "_native", False) else self._collector.fn
+        if lib().modes_resolver_run_shards(self._h, n, cp, tp, nt, bb, fn, None):
+            raise RuntimeError("modes_resolver_run_shards failed")
 
     def take_messages(self):
         out, self._collector.messages = self._collector.messages, []

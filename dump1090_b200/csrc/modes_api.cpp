@@ -491,6 +491,15 @@ int modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, con
     return 0;
 }
 
+int modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_candidate *const *candidates,
+                              const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
+                              modes_sink_fn sink, void *user) {
+    if (!r || (n_shards && (!candidates || !tiles || !n_tiles || !buffer_base))) return -1;
+    r->out.sink = sink; r->out.user = user;
+    resolve_shards(r->rs, r->rc, n_shards, candidates, tiles, n_tiles, buffer_base, r->out);
+    return 0;
+}
+
 int modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity) {
     if (!r) return -1;
     r->out.array = capacity ? out : nullptr;

@@ -87,6 +87,9 @@ struct MessageOut {
 
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
                         const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out);
+void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
+                    const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
+                    MessageOut &out);
 // The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
 int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
 

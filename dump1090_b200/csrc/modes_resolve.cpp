@@ -264,10 +264,9 @@ static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const mod
     return crcok != 0;
 }
 
-void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
-                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out) {
-    static thread_local std::vector<Delivery> deliveries;
-    deliveries.clear();
+// The verdict pass over one run of tiles: everything order-dependent, no message structs yet.
+static void judge_tiles(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
+                        size_t n_tiles, int64_t buffer_base, std::vector<Delivery> &deliveries) {
     for (size_t ti = 0; ti < n_tiles; ti++) {
         const modes_candidate *c = cands + tiles[ti].offset;
         for (uint32_t k = 0; k < tiles[ti].count; k++, c++) {
@@ -288,10 +287,11 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
             if (attempt(st, cfg, p2, true, pos, deliveries)) st.next_j = j + skip2;
         }
     }
-    static const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
-    timespec ta, tb; if (dbg) clock_gettime(CLOCK_MONOTONIC, &ta);
-    // Build the delivered structs: in place and in parallel for array output, then the
-    // callback (if any) sequentially in stream order.
+}
+
+// Build the delivered structs: in place and in parallel for array output, then the callback
+// (if any) sequentially in stream order.
+static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
     const size_t n = deliveries.size();
     size_t in_array = 0;
     if (out.array && out.count < out.capacity) {
@@ -309,7 +309,68 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
         }
     }
     out.count += n;
-    if (dbg) { clock_gettime(CLOCK_MONOTONIC, &tb); fprintf(stderr, "[resolve] %zu deliveries built in %.3f ms\n", n, (tb.tv_sec-ta.tv_sec)*1e3+(tb.tv_nsec-ta.tv_nsec)*1e-6); }
+}
+
+void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out) {
+    static thread_local std::vector<Delivery> deliveries;
+    deliveries.clear();
+    judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, deliveries);
+    deliver(deliveries, out);
+}
+
+// Several shards of one stream (e.g. one per GPU), resolved concurrently and exactly.
+//
+// The only state that crosses a shard boundary is the ICAO address cache (skip state restarts at
+// every reference buffer, and shards are whole buffers).  Shard k is therefore resolved from a
+// GUESS of the cache at its start — the cache shard k-1 ended with in the previous round — and the
+// guess is verified afterwards against the cache shard k-1 really ended with.  A shard whose guess
+// was wrong is simply resolved again.  A long shard overwrites every one of the 1024 slots many
+// times, so its final cache hardly ever depends on its initial one and two rounds normally
+// suffice; in the worst case the loop degenerates to the sequential order, never to a wrong result.
+void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
+                    const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
+                    MessageOut &out) {
+    struct Run { ResolveState start, end; std::vector<Delivery> deliveries; bool verified = false; };
+    std::vector<Run> runs(n_shards);
+    ResolveState blank;
+    blank.reset();
+    auto run_shard = [&](size_t k, const ResolveState &from) {
+        Run &r = runs[k];
+        r.start = from;
+        std::memset(r.start.stats, 0, sizeof(r.start.stats));
+        r.end = r.start;
+        r.deliveries.clear();
+        judge_tiles(r.end, cfg, cands[k], tiles[k], n_tiles[k], buffer_base[k], r.deliveries);
+    };
+    size_t done = 0;                                       // shards [0, done) are final
+    for (int round = 0; done < n_shards; round++) {
+        // fix every guess before any thread of this round starts rewriting runs[*].end
+        std::vector<ResolveState> guess(n_shards);
+        std::vector<char> rerun(n_shards, 0);
+        for (size_t k = done; k < n_shards; k++) {
+            guess[k] = (k == done) ? (done ? runs[done - 1].end : st) : (round ? runs[k - 1].end : blank);
+            rerun[k] = round == 0 || k == done || std::memcmp(guess[k].icao, runs[k].start.icao, sizeof(blank.icao)) != 0;
+        }
+        std::vector<std::thread> th;
+        for (size_t k = done; k < n_shards; k++)
+            if (rerun[k]) th.emplace_back([&, k] { run_shard(k, guess[k]); });
+        for (auto &t : th) t.join();
+        // accept the longest verified prefix
+        for (; done < n_shards; done++) {
+            const ResolveState &truth = done ? runs[done - 1].end : st;
+            if (std::memcmp(truth.icao, runs[done].start.icao, sizeof(truth.icao)) != 0) break;
+        }
+    }
+    for (size_t k = 0; k < n_shards; k++) {
+        for (int i = 0; i < 8; i++) st.stats[i] += runs[k].end.stats[i];
+        deliver(runs[k].deliveries, out);
+    }
+    if (n_shards) {
+        std::memcpy(st.icao, runs[n_shards - 1].end.icao, sizeof(st.icao));
+        st.cur_buffer = runs[n_shards - 1].end.cur_buffer;
+        st.next_j = runs[n_shards - 1].end.next_j;
+    }
 }
 
 }  // namespace modes

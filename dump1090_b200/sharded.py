@@ -70,12 +70,35 @@ def gather_records(cands, tiles, n_cand: int, dist=None, group=None, dst: int = 
     return None
 
 
+_pinned = {}
+
+
+def _to_host(t, key):
+    """Device tensor -> numpy view of a reusable pinned host buffer (async copy + one sync per call site)."""
+    import torch
+    if not t.is_cuda:
+        return t.numpy()
+    buf = _pinned.get(key)
+    if buf is None or buf.numel() < t.numel():
+        buf = torch.empty(max(t.numel(), 1), dtype=torch.uint8, pin_memory=True)
+        _pinned[key] = buf
+    buf[: t.numel()].copy_(t, non_blocking=True)
+    return buf[: t.numel()].numpy()
+
+
 def resolve_gathered(resolver, gathered, plan) -> None:
-    """Rank 0: replay the sequential half over the shards in stream order."""
-    for (c, t), (first, _n) in zip(gathered, plan):
-        c_np = c.cpu().numpy().view(api.CANDIDATE_DTYPE) if c.numel() else np.zeros(0, dtype=api.CANDIDATE_DTYPE)
-        t_np = t.cpu().numpy().view(api.TILE_DTYPE)
-        resolver.run(c_np, t_np, buffer_base=first)
+    """Rank 0: replay the sequential half over all shards (stream order).  The shards are resolved
+    concurrently on host threads; modes_resolver_run_shards keeps that exact by verifying the
+    speculated ICAO-cache state at every shard boundary."""
+    import torch
+    host = [(_to_host(c, ("c", r)), _to_host(t, ("t", r))) for r, (c, t) in enumerate(gathered)]
+    if any(c.is_cuda for c, _ in gathered):
+        torch.cuda.current_stream().synchronize()
+    shards = []
+    for (c, t), (first, _n) in zip(host, plan):
+        c_np = c.view(api.CANDIDATE_DTYPE) if c.size else np.zeros(0, dtype=api.CANDIDATE_DTYPE)
+        shards.append((c_np, t.view(api.TILE_DTYPE), first))
+    resolver.run_shards(shards)
 
 
 def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):

@@ -175,6 +175,12 @@ modes_resolver *modes_resolver_create(const modes_config *cfg);
 void modes_resolver_destroy(modes_resolver *r);
 int  modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
                         size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user);
+/* Several consecutive shards of one stream at once (one per GPU): resolved concurrently on host
+ * threads by speculating the ICAO cache at each shard boundary and verifying it; the result is
+ * identical to calling modes_resolver_run shard by shard. */
+int  modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_candidate *const *candidates,
+                               const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
+                               modes_sink_fn sink, void *user);
 int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
 int    modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity);   /* like modes_set_output */
 size_t modes_resolver_output_count(const modes_resolver *r);
