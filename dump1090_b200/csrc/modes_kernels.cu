@@ -461,10 +461,11 @@ __device__ __forceinline__ void crc_and_fix(U128 &F, int msgbits, uint32_t msgty
                                             uint32_t &crc, uint32_t &errorbit, uint32_t &nfixed) {
     const int off = 112 - msgbits;
     uint32_t acc = 0;
+    const uint32_t fw[4] = {(uint32_t)F.lo, (uint32_t)(F.lo >> 32), (uint32_t)F.hi, (uint32_t)(F.hi >> 32)};
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-        int b = 32 * r + lane;
-        if (b < msgbits && bit_of(F, b)) acc ^= s_syn[b + off];
+        const int b = 32 * r + lane;                     // bit b of the frame = bit `lane` of word r
+        if (b < msgbits && ((fw[r] >> lane) & 1u)) acc ^= s_syn[b + off];
     }
     uint32_t S = __reduce_xor_sync(0xffffffffu, acc);
     errorbit = 0xFF; nfixed = 0;
@@ -600,6 +601,7 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
             uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
     __shared__ uint32_t s_syn[112];
     __shared__ uint32_t s_hash[kFixHashSlots];
+    __shared__ __align__(8) uint32_t s_rec[16 * (kEvalThreads / 32)];
     for (int i = threadIdx.x; i < 112; i += blockDim.x) s_syn[i] = tab.bit_syn[i];
     for (int i = threadIdx.x; i < kFixHashSlots; i += blockDim.x) s_hash[i] = tab.fix_hash[i];
     __syncthreads();
@@ -745,14 +747,20 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
         }
 
         // one coalesced 56-byte record: lanes 0..13 write one word each
-        uint32_t rec[14];
-        rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
-        eval_words(P1, rec + 2);
-        eval_words(P2, rec + 8);
-        uint32_t word = 0;
+        // every lane holds the whole (warp-uniform) record; lane 0 lines it up in shared memory and
+        // lanes 0..13 store one word each: one coalesced 56-byte write
+        uint32_t *stg = s_rec + 16 * (threadIdx.x >> 5);
+        if (lane == 0) {
+            uint32_t rec[14];
+            rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
+            eval_words(P1, rec + 2);
+            eval_words(P2, rec + 8);
 #pragma unroll
-        for (int k = 0; k < 14; k++) word = (lane == k) ? rec[k] : word;
-        if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = word;
+            for (int k = 0; k < 14; k += 2) *reinterpret_cast<uint2 *>(stg + k) = make_uint2(rec[k], rec[k + 1]);
+        }
+        __syncwarp();
+        if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = stg[lane];
+        __syncwarp();
         cur = nxt;
     }
 }
