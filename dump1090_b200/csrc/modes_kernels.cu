@@ -616,11 +616,17 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
     const uint32_t stride = gridDim.x * warps_per_block;
     uint32_t ci = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
     RawWindow cur;
+    uint32_t v1 = 0;                                      // position of candidate ci + stride
     if (ci < n_cand) load_window(in, cand_v[ci], lane, cur);
+    if (ci + stride < n_cand) v1 = cand_v[ci + stride];
     for (; ci < n_cand; ci += stride) {
+        // two dependent HBM round trips (position, then samples) are both kept off the critical
+        // path: positions are fetched two candidates ahead, sample words one candidate ahead
         RawWindow nxt;
         nxt.v = 0;
-        if (ci + stride < n_cand) load_window(in, cand_v[ci + stride], lane, nxt);
+        if (ci + stride < n_cand) load_window(in, v1, lane, nxt);
+        uint32_t v2 = 0;
+        if (ci + 2 * stride < n_cand) v2 = cand_v[ci + 2 * stride];
 
         const uint32_t v = cur.v;
         const uint64_t t = (uint64_t)v - 2;
@@ -762,6 +768,7 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
         if (lane < 14) reinterpret_cast<uint32_t *>(records + ci)[lane] = stg[lane];
         __syncwarp();
         cur = nxt;
+        v1 = v2;
     }
 }
 
