@@ -37,6 +37,9 @@ struct Slot {
     bool busy = false;
     size_t n_buffers = 0;
     int64_t buffer_base = 0;
+    const void *batch_iq = nullptr;   // device address the batch was scanned from
+    bool own_outputs = true;          // results in this slot's own buffers (growable)
+    uint32_t want_cap = 0;            // grow the candidate buffers to at least this on the next ensure
     // where this batch's results live (own workspace unless the caller supplied memory)
     modes_candidate *out_records = nullptr;
     modes_tile *out_tiles = nullptr;
@@ -125,6 +128,7 @@ int slot_ensure(modes_ctx *ctx, Slot &s, uint64_t n_samples, bool need_iq, bool 
         s.iq_bytes = n_samples * 2;
     }
     uint32_t cap = default_cand_capacity(n_samples);
+    if (cap < s.want_cap) cap = s.want_cap;
     if (s.cand_cap < cap) {
         cudaFree(s.d_cand_v); s.d_cand_v = nullptr;
         cudaFree(s.d_records); s.d_records = nullptr;
@@ -157,6 +161,8 @@ int host_ensure(modes_ctx *ctx, Slot &s, size_t n_records, size_t n_tiles) {
     return 0;
 }
 
+int launch_batch(modes_ctx *ctx, Slot &s);
+
 // Queue one batch on the slot's stream: (optional H2D) + halo + scan + frame evaluation.
 int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, size_t n_buffers,
            const uint8_t *carry476, modes_candidate *d_records_ext, uint32_t cap_ext, modes_tile *d_tiles_ext) {
@@ -171,12 +177,20 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
     memset(s.h_halo, 127, kHaloBytes);                                    // dump1090.c:344 no-signal
     if (carry476) memcpy(s.h_halo + (kHaloBytes - MODES_CARRY_BYTES), carry476, MODES_CARRY_BYTES);
     CK(ctx, cudaMemcpyAsync(s.d_halo, s.h_halo, kHaloBytes, cudaMemcpyHostToDevice, s.stream));
-    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(uint32_t), s.stream));
-
-    BatchView in{static_cast<const uint8_t *>(d_iq), s.d_halo, n_samples};
+    s.batch_iq = d_iq;
+    s.n_buffers = n_buffers;
+    s.own_outputs = d_records_ext == nullptr;
     s.out_records = d_records_ext ? d_records_ext : s.d_records;
     s.out_tiles = d_tiles_ext ? d_tiles_ext : s.d_tiles;
     s.out_cap = d_records_ext ? (cap_ext < s.cand_cap ? cap_ext : s.cand_cap) : s.cand_cap;
+    return launch_batch(ctx, s);
+}
+
+// The two kernels over the slot's staged batch (also used to repeat a batch that overflowed).
+int launch_batch(modes_ctx *ctx, Slot &s) {
+    const uint64_t n_samples = (uint64_t)s.n_buffers * kBufSamples;
+    CK(ctx, cudaMemsetAsync(s.d_counters, 0, 4 * sizeof(uint32_t), s.stream));
+    BatchView in{static_cast<const uint8_t *>(s.batch_iq), s.d_halo, n_samples};
     ScanOutputs so{s.d_cand_v, s.out_cap, s.out_tiles, s.d_counters};
 
     cudaEvent_t *pe = nullptr;
@@ -199,15 +213,25 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
     CK(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaEventRecord(s.ev[3], s.stream));
     s.busy = true;
-    s.n_buffers = n_buffers;
     return 0;
 }
 
-// Wait for the slot's batch; returns the number of candidates stored.
+// Wait for the slot's batch; returns the number of candidates stored.  A batch denser than the
+// candidate buffers (default: one candidate per 64 samples) is repeated with larger buffers when
+// they are the slot's own; caller-supplied buffers cannot grow and report the overflow.
 int wait_batch(modes_ctx *ctx, Slot &s, uint64_t *n_out) {
-    CK(ctx, cudaEventSynchronize(s.ev[3]));
-    if (s.h_counters[1] || s.h_counters[0] > s.out_cap)
-        return fail(ctx, "candidate capacity exceeded: %u found, room for %u", s.h_counters[0], s.out_cap);
+    for (;;) {
+        CK(ctx, cudaEventSynchronize(s.ev[3]));
+        if (!s.h_counters[1] && s.h_counters[0] <= s.out_cap) break;
+        const uint32_t found = s.h_counters[0];
+        if (!s.own_outputs)
+            return fail(ctx, "candidate capacity exceeded: %u found, room for %u", found, s.out_cap);
+        s.want_cap = found + found / 8 + 1024;
+        if (slot_ensure(ctx, s, (uint64_t)s.n_buffers * kBufSamples, false, true)) return -1;
+        s.out_records = s.d_records;
+        s.out_cap = s.cand_cap;
+        if (launch_batch(ctx, s)) return -1;
+    }
     *n_out = s.h_counters[0];
     return 0;
 }

@@ -145,3 +145,54 @@ def test_full_size_properties(gpu_decoder_factory, checker_libs):
     assert dec2.output_count() == n
     assert hashlib.sha256(b"".join(bytes(out2[i].msg) for i in range(n))).hexdigest() == digest
     assert dec2.stats() == stats
+
+
+def _periodic(period_pattern, nsamples, amp=100):
+    """I/Q stream whose magnitude repeats `period_pattern` (1 = pulse, 0 = silence)."""
+    pat = np.array(period_pattern, dtype=np.uint8)
+    reps = -(-nsamples // pat.size)
+    hi = np.tile(pat, reps)[:nsamples]
+    out = np.full(2 * nsamples, 127, dtype=np.uint8)
+    out[0::2] = 127 + amp * hi
+    return out
+
+
+@pytest.mark.parametrize("name,pattern", [
+    ("candidate_every_15", [1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0]),      # > 256 candidates per 4096-tile
+    ("survivor_every_7", [1, 0, 1, 0, 0, 0, 0]),                                 # > 512 ten-comparison survivors per tile
+    ("candidate_every_16", [1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0, 0]),   # exactly 256 per tile
+])
+def test_pathological_density(name, pattern, gpu_decoder_factory, checker_libs):
+    """Periodic input that makes (almost) every period a preamble: the scan kernel's dense path,
+    and the automatic growth of the candidate buffers (default room: one candidate per 64 samples)."""
+    import torch
+    data = _periodic(pattern, 131072 * 2 + 5000)
+    exp, st = C.oracle_decode(data, check_crc=0)
+    dec = gpu_decoder_factory(check_crc=0)
+    got = dec.decode(data)
+    assert [m.raw_line() for m in got] == [m.hexline() for m in exp]
+    assert list(dec.stats().values()) == st
+    # candidate records, byte for byte
+    nbuf = data.size // api.BUFFER_BYTES + 1
+    padded = np.full(nbuf * api.BUFFER_BYTES, 127, dtype=np.uint8)
+    padded[: data.size] = data
+    want = C.oracle_scan_candidates(data, cap=200000)
+    want_arr = np.frombuffer(b"".join(bytes(c) for c in want), dtype=api.CANDIDATE_DTYPE)
+    d = torch.from_numpy(padded).cuda()
+    dec.detect_device(d.data_ptr(), nbuf)
+    cands, tiles = dec.detect_fetch(nbuf)
+    order = np.concatenate([np.arange(o, o + c) for o, c in tiles]).astype(int)
+    assert order.size == want_arr.size
+    assert np.array_equal(cands.view(np.uint8).reshape(-1, 56)[order], want_arr.view(np.uint8).reshape(-1, 56))
+
+
+def test_caller_buffers_overflow_is_reported(gpu_decoder_factory):
+    import torch
+    data = _periodic([1, 0, 1, 0, 0, 0, 0, 1, 0, 1, 0, 0, 0, 0, 0], 131072)
+    d = torch.from_numpy(data).cuda()
+    small = torch.zeros(100 * 56, dtype=torch.uint8, device="cuda")
+    tiles = torch.zeros(api.tiles_for(1) * 8, dtype=torch.uint8, device="cuda")
+    dec = gpu_decoder_factory()
+    dec.detect_device(d.data_ptr(), 1, None, small.data_ptr(), 100, tiles.data_ptr())
+    with pytest.raises(RuntimeError, match="capacity exceeded"):
+        dec.detect_wait()
