@@ -167,7 +167,7 @@ def test_pathological_density(name, pattern, gpu_decoder_factory, checker_libs):
     and the automatic growth of the candidate buffers (default room: one candidate per 64 samples)."""
     import torch
     data = _periodic(pattern, 131072 * 2 + 5000)
-    exp, st = C.oracle_decode(data, check_crc=0)
+    exp, st = C.oracle_decode(data, check_crc=0, cap=200000)
     dec = gpu_decoder_factory(check_crc=0)
     got = dec.decode(data)
     assert [m.raw_line() for m in got] == [m.hexline() for m in exp]
