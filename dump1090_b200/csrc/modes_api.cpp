@@ -249,6 +249,7 @@ int collect(modes_ctx *ctx, Slot &s) {
     static const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
     const double t0 = dbg ? now_ms() : 0;
     if (wait_batch(ctx, s, &n)) return -1;
+    s.busy = false;                                     // a repeated (overflowed) batch re-arms the flag
     const double t1 = dbg ? now_ms() : 0;
     const size_t nt = tiles_for((uint64_t)s.n_buffers * kBufSamples);
     if (host_ensure(ctx, s, n, nt)) return -1;
