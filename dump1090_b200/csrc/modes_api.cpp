@@ -102,9 +102,9 @@ uint32_t default_cand_capacity(uint64_t n_samples) {
 
 int slot_init(modes_ctx *ctx, Slot &s) {
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    CK(ctx, cudaMalloc(&s.d_halo, kHaloBytes));
+    CK(ctx, cudaMalloc(&s.d_halo, kHaloAlloc));
     CK(ctx, cudaMalloc(&s.d_counters, 4 * sizeof(uint32_t)));
-    CK(ctx, cudaMallocHost(&s.h_halo, kHaloBytes));
+    CK(ctx, cudaMallocHost(&s.h_halo, kHaloAlloc));
     CK(ctx, cudaMallocHost(&s.h_counters, 4 * sizeof(uint32_t)));
     for (auto &e : s.ev) CK(ctx, cudaEventCreate(&e));
     return 0;
@@ -174,9 +174,9 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
         d_iq = s.d_iq;
     }
     if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0) return fail(ctx, "device I/Q pointer must be 16-byte aligned");
-    memset(s.h_halo, 127, kHaloBytes);                                    // dump1090.c:344 no-signal
+    memset(s.h_halo, 127, kHaloAlloc);                                    // dump1090.c:344 no-signal
     if (carry476) memcpy(s.h_halo + (kHaloBytes - MODES_CARRY_BYTES), carry476, MODES_CARRY_BYTES);
-    CK(ctx, cudaMemcpyAsync(s.d_halo, s.h_halo, kHaloBytes, cudaMemcpyHostToDevice, s.stream));
+    CK(ctx, cudaMemcpyAsync(s.d_halo, s.h_halo, kHaloAlloc, cudaMemcpyHostToDevice, s.stream));
     s.batch_iq = d_iq;
     s.n_buffers = n_buffers;
     s.own_outputs = d_records_ext == nullptr;

@@ -21,6 +21,7 @@ namespace modes {
 // and the scan visits j in [0, 131070) (dump1090.c:1593).
 constexpr int      kHaloSamples  = 240;
 constexpr int      kHaloBytes    = 480;
+constexpr int      kHaloAlloc    = 512;                         // + 16 bytes of "no signal" (127) after the carry: kernels read it for out-of-range chunks
 constexpr int      kTileSamples  = MODES_TILE_SAMPLES;          // one scan tile
 constexpr uint32_t kBufSamples   = MODES_BUFFER_SAMPLES;
 constexpr uint32_t kScanLimit    = kBufSamples - 2;             // j < 131070
