@@ -110,15 +110,17 @@ __device__ __forceinline__ uint32_t n2_pack15(uint32_t raw) {
     return __vminu2(n0 + ((nt - n0) << 16), kK15);
 }
 
-// 16-byte chunk `chunk` (0..514) of the tile whose first virtual chunk is c0: one unconditional
-// load from a selected address — carry block, body, or the 16 "no signal" bytes kept after the
-// carry block for chunks past the end of the batch.
-__device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, uint32_t c0, int chunk, uint32_t n_vchunks) {
-    const uint32_t c = c0 + (uint32_t)chunk;
-    const uint8_t *p = in.body + 16ull * (c - kHaloSamples / 8);
-    if (c < kHaloSamples / 8) p = in.halo + 16 * c;
-    if (c >= n_vchunks) p = in.halo + kHaloBytes;
-    return ldg_stream(reinterpret_cast<const uint4 *>(p));
+// Where a tile's samples live: interior tiles (the common case) are one flat run of the
+// body; the first tile starts in the carry block and the last one ends the batch.
+struct TileSrc {
+    const uint8_t *flat;         // address of tile sample 0 when the tile (+24 lookahead samples) is interior
+    uint64_t c0;                 // first virtual chunk of the tile
+    bool interior;
+};
+
+__device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
+    if (t.interior) return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+    return load_vchunk(in, t.c0 + chunk, n_vchunks);
 }
 
 // Squared magnitude of tile sample s (0 .. 4096+23) from the warp's shared-memory copy.
@@ -210,6 +212,14 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
         Pc[0] = Pn[0]; Pc[1] = Pn[1]; Pc[2] = Pn[2]; Pc[3] = Pn[3];                                                \
     }
 
+__device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, uint64_t n_vchunks) {
+    TileSrc ts;
+    ts.c0 = (uint64_t)g * kTileChunks;
+    ts.interior = ts.c0 >= kHaloSamples / 8 && ts.c0 + kTileChunks + 3 <= n_vchunks;
+    ts.flat = in.body + 16 * (ts.c0 - kHaloSamples / 8);
+    return ts;
+}
+
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -220,13 +230,13 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
     uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
 
     const int lane = threadIdx.x;
-    const uint32_t n_vchunks = (uint32_t)((in.n_samples + kHaloSamples) / 8);
+    const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
     const uint64_t t_end = in.n_samples;
 
     // rows 0..3 of the first tile
     uint32_t g = blockIdx.x;
     if (g >= n_tiles) return;
-    uint32_t ts = g * (uint32_t)kTileChunks;                 // first virtual chunk of the tile being loaded
+    TileSrc ts = tile_source(in, g, n_vchunks);
     uint4 x0 = load_row_chunk(in, ts, lane, n_vchunks), x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
     uint4 x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
 
@@ -261,7 +271,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
         // ---- start the next tile's first four rows now; they arrive while this tile is finished
         const uint32_t g_next = g + gridDim.x;
         if (g_next < n_tiles) {
-            ts = g_next * (uint32_t)kTileChunks;
+            ts = tile_source(in, g_next, n_vchunks);
             x0 = load_row_chunk(in, ts, lane, n_vchunks); x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
             x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks); x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
         }
