@@ -84,8 +84,8 @@ __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
 // Arithmetic: squared magnitudes n = i*i+q*q are held two per 32-bit register as
 // 15-bit fields (n clamped to 32767, order preserving on the reachable values), so one
 // 32-bit instruction works on two positions:
-//     cX      = 0x7fff7fff - X          (complement, per half)
-//     L + cR  has bit 15 / bit 31 set   <=>  L > R   in the low / high half
+//     L + 0x7fff7fff - R  has bit 15 / bit 31 set   <=>  L > R   in the low / high half
+//     (one three-input add; no borrow or carry crosses the halves because both are <= 0x7fff)
 // The ten comparisons of dump1090.c:1602-1611 for position j reduce to
 //     min(m0,m2) > max(m1,m3)      m0 > max(m4,m5,m6)
 //     m9 > max(m6,m8)              m7 > m8
@@ -196,13 +196,12 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
             const uint32_t S0 = __byte_perm(P[u], P[u + 1], 0x5432), S1 = __byte_perm(P[u + 1], P[u + 2], 0x5432); \
             const uint32_t S2 = __byte_perm(P[u + 2], P[u + 3], 0x5432);                                           \
             const uint32_t S3 = __byte_perm(P[u + 3], P[u + 4], 0x5432), S4 = __byte_perm(P[u + 4], P[u + 5], 0x5432); \
-            const uint32_t cS0 = kK15 - S0, cS1 = kK15 - S1, cS2 = kK15 - S2;                                      \
-            const uint32_t cP2 = kK15 - P[u + 2], cP3 = kK15 - P[u + 3], cP4 = kK15 - P[u + 4];                    \
-            const uint32_t A = __vminu2(P[u], P[u + 1]);        /* min(m0, m2)          */                         \
-            const uint32_t cB = __vminu2(cS0, cS1);             /* K - max(m1, m3)      */                         \
-            const uint32_t cW = __vimin3_u16x2(cP2, cS2, cP3);  /* K - max(m4, m5, m6)  */                         \
-            const uint32_t cE = __vminu2(cP3, cP4);             /* K - max(m6, m8)      */                         \
-            const uint32_t D1 = A + cB, D2 = P[u] + cW, D3 = S4 + cE, D4 = S3 + cP4;                               \
+            const uint32_t A = __vminu2(P[u], P[u + 1]);             /* min(m0, m2)     */                         \
+            const uint32_t B = __vmaxu2(S0, S1);                     /* max(m1, m3)     */                         \
+            const uint32_t W = __vimax3_u16x2(P[u + 2], S2, P[u + 3]); /* max(m4, m5, m6) */                       \
+            const uint32_t E = __vmaxu2(P[u + 3], P[u + 4]);         /* max(m6, m8)     */                         \
+            /* L + 0x7fff - R per 16-bit half: bit 15 set <=> L > R; no borrow or carry between halves */         \
+            const uint32_t D1 = A + kK15 - B, D2 = P[u] + kK15 - W, D3 = S4 + kK15 - E, D4 = S3 + kK15 - P[u + 4]; \
             T[u] = D1 & D2 & D3 & D4;                           /* bit 15 / 31: position 2u / 2u+1 passes */       \
         }                                                                                                          \
         const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);                   \
