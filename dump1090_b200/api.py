@@ -95,7 +95,9 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
            "modes_resolver_run_shards", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
-           "modes_set_output", "modes_output_count", "modes_host_alloc",
+           "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
+           "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
+           "modes_detect_publish_count", "modes_host_alloc",
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
 
 
@@ -140,6 +142,16 @@ def lib():
         L.modes_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.modes_output_count.restype = C.c_size_t
         L.modes_output_count.argtypes = [C.c_void_p]
+        L.modes_device_alloc.restype = C.c_void_p
+        L.modes_device_alloc.argtypes = [C.c_size_t]
+        L.modes_device_free.argtypes = [C.c_void_p]
+        L.modes_ipc_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.modes_ipc_open.restype = C.c_void_p
+        L.modes_ipc_open.argtypes = [C.c_void_p]
+        L.modes_ipc_close.argtypes = [C.c_void_p]
+        L.modes_detect_publish_count.argtypes = [C.c_void_p, C.c_void_p]
+        L.modes_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_device_memset.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
         L.modes_host_alloc.restype = C.c_void_p
         L.modes_host_alloc.argtypes = [C.c_size_t]
         L.modes_host_free.argtypes = [C.c_void_p]
@@ -334,6 +346,9 @@ class Decoder:
         m = Message()
         self._check(lib().modes_decode_frame(self._h, buf, C.byref(m)))
         return m
+
+    def publish_count(self, dst_ptr: int) -> None:
+        self._check(lib().modes_detect_publish_count(self._h, C.c_void_p(dst_ptr)))
 
     def kernel_times_ms(self):
         t = (C.c_float * 4)()

@@ -562,6 +562,47 @@ int modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out
 
 void *modes_stream(modes_ctx *ctx) { return ctx ? (void *)ctx->detect.stream : nullptr; }
 
+void *modes_device_alloc(size_t nbytes) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, nbytes ? nbytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+
+void modes_device_free(void *p) { if (p) cudaFree(p); }
+
+int modes_ipc_export(const void *dptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (!dptr || cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)) != cudaSuccess) return -1;
+    memcpy(handle, &h, 64);
+    return 0;
+}
+
+void *modes_ipc_open(const uint8_t handle[64]) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+int modes_ipc_close(void *mapped) { return mapped && cudaIpcCloseMemHandle(mapped) == cudaSuccess ? 0 : -1; }
+
+int modes_copy_to_host(void *dst_host, const void *src_device, size_t nbytes) {
+    return cudaMemcpy(dst_host, src_device, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+}
+
+int modes_device_memset(void *dst_device, int value, size_t nbytes) {
+    if (cudaMemset(dst_device, value, nbytes) != cudaSuccess) return -1;
+    return cudaDeviceSynchronize() == cudaSuccess ? 0 : -1;
+}
+
+int modes_detect_publish_count(modes_ctx *ctx, void *dst) {
+    if (!ctx || !dst) return -1;
+    CK(ctx, cudaMemcpyAsync(dst, ctx->detect.d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->detect.stream));
+    return 0;
+}
+
 void *modes_host_alloc(size_t nbytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, nbytes ? nbytes : 1) != cudaSuccess) return nullptr;

@@ -109,3 +109,97 @@ def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):
     w1 = dist.gather(cands, out[0] if rank == dst else None, dst=dst, group=group, async_op=True)
     w2 = dist.gather(tiles, out[1] if rank == dst else None, dst=dst, group=group, async_op=True)
     return w1, w2
+
+
+class PeerGather:
+    """Record gather fused into the kernels: every rank's scan / frame-evaluation kernels store
+    their tile table and candidate records straight into a buffer in rank 0's HBM (mapped through
+    CUDA IPC, written over NVLink), so no collective follows the compute.  The only collective left
+    is a 4-byte all-reduce that tells rank 0 the peers' kernels have finished.
+
+    Layout of one buffer: world segments of [16-byte header {found, overflow, 0, 0}][tile table]
+    [records]; `nbuf` double-buffers so that rank 0 can read step i while step i+1 is written.
+    """
+
+    def __init__(self, dist, rank: int, world: int, n_buffers_per_rank: int, cap: int, nbuf: int = 2, group=None):
+        import torch
+        self.dist, self.rank, self.world, self.cap, self.group = dist, rank, world, cap, group
+        self.n_tiles = api.tiles_for(n_buffers_per_rank)
+        self.tiles_off = 16
+        self.rec_off = (16 + self.n_tiles * 8 + 255) // 256 * 256
+        self.seg = (self.rec_off + cap * 56 + 255) // 256 * 256
+        self.buf_bytes = self.seg * world
+        self.nbuf = nbuf
+        L = api.lib()
+        handle = torch.zeros(64, dtype=torch.uint8)
+        self._own = None
+        if rank == 0:
+            self._own = L.modes_device_alloc(self.buf_bytes * nbuf)
+            if not self._own:
+                raise MemoryError("modes_device_alloc failed")
+            hb = (api.C.c_uint8 * 64)()
+            if L.modes_ipc_export(api.C.c_void_p(self._own), hb):
+                raise RuntimeError("modes_ipc_export failed")
+            handle = torch.tensor(list(hb), dtype=torch.uint8)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        h = handle.to(dev)
+        dist.broadcast(h, src=0, group=group)
+        if rank == 0:
+            self.base = self._own
+        else:
+            hb = (api.C.c_uint8 * 64)(*h.cpu().tolist())
+            self.base = L.modes_ipc_open(hb)
+            if not self.base:
+                raise RuntimeError("modes_ipc_open failed (no peer access to rank 0?)")
+        self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def segment(self, k: int, rank: int | None = None):
+        """(header_ptr, tiles_ptr, records_ptr) of `rank`'s segment in buffer k."""
+        r = self.rank if rank is None else rank
+        b = self.base + (k % self.nbuf) * self.buf_bytes + r * self.seg
+        return b, b + self.tiles_off, b + self.rec_off
+
+    def detect(self, dec, d_iq_ptr: int, n_buffers: int, carry, k: int) -> None:
+        """Launch this rank's kernels with their outputs in rank 0's memory, then publish the count."""
+        hdr, tiles, recs = self.segment(k)
+        dec.detect_device(d_iq_ptr, n_buffers, carry, recs, self.cap, tiles)
+        dec.publish_count(hdr)
+
+    def fence(self):
+        """All ranks: after this (stream-ordered) every rank's kernels up to here have completed."""
+        return self.dist.all_reduce(self._flag, group=self.group, async_op=True)
+
+    def fetch(self, k: int):
+        """Rank 0, after fence().wait() and a stream sync: [(cands ndarray, tiles ndarray)] per rank."""
+        import torch
+        assert self.rank == 0
+        out = []
+        hdrs = np.zeros((self.world, 4), dtype=np.uint32)
+        L = api.lib()
+        def d2h(dst, src, n):
+            if L.modes_copy_to_host(api.C.c_void_p(dst), api.C.c_void_p(src), n):
+                raise RuntimeError("device-to-host copy failed")
+        for r in range(self.world):
+            hdr, tiles, recs = self.segment(k, r)
+            d2h(hdrs[r].ctypes.data, hdr, 16)
+        for r in range(self.world):
+            n, ovf = int(hdrs[r][0]), int(hdrs[r][1])
+            if ovf or n > self.cap:
+                raise RuntimeError(f"rank {r}: candidate capacity exceeded ({n} > {self.cap})")
+            hdr, tiles, recs = self.segment(k, r)
+            t = np.empty(self.n_tiles, dtype=api.TILE_DTYPE)
+            c = np.empty(max(n, 1), dtype=api.CANDIDATE_DTYPE)
+            d2h(t.ctypes.data, tiles, t.nbytes)
+            if n:
+                d2h(c.ctypes.data, recs, n * 56)
+            out.append((c[:n], t))
+        return out
+
+    def close(self):
+        L = api.lib()
+        if self.rank == 0 and self._own:
+            L.modes_device_free(self._own)
+            self._own = None
+        elif self.rank != 0 and self.base:
+            L.modes_ipc_close(self.base)
+            self.base = None

@@ -193,6 +193,21 @@ int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *ou
 /* ---- plumbing ----------------------------------------------------------- */
 void *modes_stream(modes_ctx *ctx);                    /* the cudaStream_t modes_detect_device launches on */
 int   modes_set_stream(modes_ctx *ctx, void *cuda_stream);   /* use the caller's stream for it (NULL: own) */
+/* Device memory that other ranks on the same node can write into (CUDA IPC): rank 0 of a
+ * multi-GPU job allocates the gather buffer with modes_device_alloc, exports it, and every other
+ * rank maps it and passes its segment as d_candidates / d_tiles of modes_detect_device, so the
+ * frame-evaluation kernel stores its records straight into rank 0's HBM over NVLink — the record
+ * gather is fused into the kernel instead of following it as a collective. */
+void *modes_device_alloc(size_t nbytes);
+void  modes_device_free(void *p);
+int   modes_ipc_export(const void *dptr, uint8_t handle[64]);
+void *modes_ipc_open(const uint8_t handle[64]);          /* on the importing rank's current device */
+int   modes_ipc_close(void *mapped);
+int   modes_copy_to_host(void *dst_host, const void *src_device, size_t nbytes);   /* synchronous */
+int   modes_device_memset(void *dst_device, int value, size_t nbytes);            /* synchronous */
+/* Queue a device-to-device copy of the last modes_detect_device's counters {found, overflow,0,0}
+ * (16 bytes) to `dst` (may be peer memory) on the detect stream. */
+int   modes_detect_publish_count(modes_ctx *ctx, void *dst);
 void *modes_host_alloc(size_t nbytes);                 /* pinned host memory for modes_process input */
 void  modes_host_free(void *p);
 /* cfg.profile: mean device time (CUDA events on the launching stream) per batch

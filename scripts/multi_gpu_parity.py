@@ -27,6 +27,20 @@ for seed, nsamples, kw in [(41, 131072 * 7 + 5000, {}), (42, 131072 * 4, dict(ag
     else:
         d_t = d_t[:0]
     g = sharded.gather_records(d_c, d_t, n, dist)
+    # the same job with the gather fused into the kernels (records written into rank 0's HBM)
+    nb_max = max(c for _, c in plan)
+    pg = sharded.PeerGather(dist, rank, world, nb_max, nb_max * api.BUFFER_SAMPLES // 64 + 4096)
+    if count:
+        pg.detect(dec, shard.data_ptr(), count, sharded.carry_before(padded, first), 0)
+        dec.detect_wait()
+    else:
+        api.lib().modes_device_memset(api.C.c_void_p(pg.segment(0)[0]), 0, 16)
+    pg.fence().wait(); torch.cuda.synchronize()
+    if rank == 0:
+        fused = pg.fetch(0)
+        res2 = api.Resolver(**kw); res2.set_output_array(200000)
+        res2.run_shards([(c, (t if plan[r][1] else t[:0]), plan[r][0]) for r, (c, t) in enumerate(fused)])
+        lines2 = [res2._out[i].raw_line() for i in range(res2.output_count())]
     if rank == 0:
         res = api.Resolver(**kw); res.set_output_array(200000)
         sharded.resolve_gathered(res, g, plan)
@@ -34,8 +48,10 @@ for seed, nsamples, kw in [(41, 131072 * 7 + 5000, {}), (42, 131072 * 4, dict(ag
         okw = dict(fix=kw.get("fix_errors", 1), aggressive=kw.get("aggressive", 0))
         exp, st = C.oracle_decode(data, **okw)
         ok = lines == [m.hexline() for m in exp] and list(res.stats().values()) == st
+        ok = ok and lines2 == lines and res2.stats() == res.stats()
         ok_all &= ok
         print(f"world={world} seed={seed} buffers={nbuf_total} msgs={len(lines)} parity={'OK' if ok else 'MISMATCH'}", flush=True)
+    dist.barrier(); pg.close()
     dec.close()
 dist.barrier()
 if rank == 0:
