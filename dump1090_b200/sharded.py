@@ -152,6 +152,9 @@ class PeerGather:
             if not self.base:
                 raise RuntimeError("modes_ipc_open failed (no peer access to rank 0?)")
         self._flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._pin = None
+        if rank == 0:                                   # pinned landing zone for fetch()
+            self._pin = api.PinnedBuffer(world * (self.n_tiles * 8 + cap * 56))
 
     def segment(self, k: int, rank: int | None = None):
         """(header_ptr, tiles_ptr, records_ptr) of `rank`'s segment in buffer k."""
@@ -187,8 +190,9 @@ class PeerGather:
             if ovf or n > self.cap:
                 raise RuntimeError(f"rank {r}: candidate capacity exceeded ({n} > {self.cap})")
             hdr, tiles, recs = self.segment(k, r)
-            t = np.empty(self.n_tiles, dtype=api.TILE_DTYPE)
-            c = np.empty(max(n, 1), dtype=api.CANDIDATE_DTYPE)
+            off = r * (self.n_tiles * 8 + self.cap * 56)
+            t = self._pin.array[off: off + self.n_tiles * 8].view(api.TILE_DTYPE)
+            c = self._pin.array[off + self.n_tiles * 8: off + self.n_tiles * 8 + max(n, 1) * 56].view(api.CANDIDATE_DTYPE)
             d2h(t.ctypes.data, tiles, t.nbytes)
             if n:
                 d2h(c.ctypes.data, recs, n * 56)
@@ -200,6 +204,7 @@ class PeerGather:
         if self.rank == 0 and self._own:
             L.modes_device_free(self._own)
             self._own = None
+            self._pin.free()
         elif self.rank != 0 and self.base:
             L.modes_ipc_close(self.base)
             self.base = None
