@@ -92,9 +92,9 @@ _lib = None
 # every symbol include/modes_b200.h declares
 EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_destroy", "modes_last_error",
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
-           "modes_compute_magnitude", "modes_detect_device", "modes_detect_wait", "modes_detect_fetch",
+           "modes_compute_magnitude", "modes_detect_device", "modes_detect_host", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_run_shards", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
@@ -121,6 +121,8 @@ def lib():
         L.modes_compute_magnitude.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.modes_detect_device.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                           C.c_size_t, C.c_void_p]
+        L.modes_detect_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                        C.c_size_t, C.c_void_p]
         L.modes_detect_wait.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.modes_detect_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.modes_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]
@@ -131,6 +133,7 @@ def lib():
                                          C.c_void_p]
         L.modes_resolver_run_shards.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_void_p, SINK_FN, C.c_void_p]
+        L.modes_resolver_reset.argtypes = [C.c_void_p]
         L.modes_resolver_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         L.modes_resolver_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.modes_resolver_output_count.restype = C.c_size_t
@@ -325,6 +328,12 @@ class Decoder:
                                               C.c_void_p(d_candidates_ptr), cand_capacity,
                                               C.c_void_p(d_tiles_ptr)))
 
+    def detect_host(self, host_ptr: int, n_buffers: int, carry: bytes | None = None,
+                    d_candidates_ptr: int = 0, cand_capacity: int = 0, d_tiles_ptr: int = 0) -> None:
+        carr = (C.c_uint8 * CARRY_BYTES).from_buffer_copy(carry) if carry is not None else None
+        self._check(lib().modes_detect_host(self._h, C.c_void_p(host_ptr), n_buffers, carr,
+                                            C.c_void_p(d_candidates_ptr), cand_capacity, C.c_void_p(d_tiles_ptr)))
+
     def detect_wait(self) -> int:
         n = C.c_uint64(0)
         self._check(lib().modes_detect_wait(self._h, C.byref(n)))
@@ -378,6 +387,9 @@ class Resolver:
         rc = lib().modes_resolver_run(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base, fn, None)
         if rc:
             raise RuntimeError("modes_resolver_run failed")
+
+    def reset_state(self) -> None:
+        lib().modes_resolver_reset(self._h)
 
     def run_shards(self, shards) -> None:
         """shards: [(cands ndarray, tiles ndarray, buffer_base)] in stream order; resolved concurrently."""

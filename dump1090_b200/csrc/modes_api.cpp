@@ -462,6 +462,16 @@ int modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, cons
                   static_cast<modes_candidate *>(d_candidates), cap, static_cast<modes_tile *>(d_tiles));
 }
 
+int modes_detect_host(modes_ctx *ctx, const uint8_t *iq, size_t n_buffers, const uint8_t *carry476,
+                      void *d_candidates, size_t cand_capacity, void *d_tiles) {
+    if (!ctx) return -1;
+    if (!iq || !n_buffers) return fail(ctx, "modes_detect_host: empty input");
+    CK(ctx, cudaSetDevice(ctx->cfg.device));
+    uint32_t cap = cand_capacity > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)cand_capacity;
+    return submit(ctx, ctx->detect, iq, nullptr, n_buffers, carry476,
+                  static_cast<modes_candidate *>(d_candidates), cap, static_cast<modes_tile *>(d_tiles));
+}
+
 int modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates) {
     if (!ctx) return -1;
     if (!ctx->detect.busy) return fail(ctx, "modes_detect_wait without modes_detect_device");
@@ -535,6 +545,12 @@ int modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capa
 
 size_t modes_resolver_output_count(const modes_resolver *r) { return r ? r->out.count : 0; }
 
+int modes_resolver_reset(modes_resolver *r) {
+    if (!r) return -1;
+    r->rs.reset();
+    return 0;
+}
+
 int modes_resolver_stats(const modes_resolver *r, modes_stats *out) {
     if (!r || !out) return -1;
     memcpy(out->v, r->rs.stats, sizeof(out->v));
@@ -589,7 +605,18 @@ void *modes_ipc_open(const uint8_t handle[64]) {
 int modes_ipc_close(void *mapped) { return mapped && cudaIpcCloseMemHandle(mapped) == cudaSuccess ? 0 : -1; }
 
 int modes_copy_to_host(void *dst_host, const void *src_device, size_t nbytes) {
-    return cudaMemcpy(dst_host, src_device, nbytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -1;
+    // own non-blocking stream per calling thread: never serialises with the caller's other streams
+    static thread_local cudaStream_t st = nullptr;
+    static thread_local int st_dev = -1;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, src_device) != cudaSuccess) return -1;
+    if (cudaSetDevice(at.device) != cudaSuccess) return -1;
+    if (!st || st_dev != at.device) {
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return -1;
+        st_dev = at.device;
+    }
+    if (cudaMemcpyAsync(dst_host, src_device, nbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
 }
 
 int modes_device_memset(void *dst_device, int value, size_t nbytes) {

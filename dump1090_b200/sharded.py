@@ -168,6 +168,12 @@ class PeerGather:
         dec.detect_device(d_iq_ptr, n_buffers, carry, recs, self.cap, tiles)
         dec.publish_count(hdr)
 
+    def detect_host(self, dec, host_ptr: int, n_buffers: int, carry, k: int) -> None:
+        """Same from (pinned) host memory: H2D + kernels on the decoder's stream."""
+        hdr, tiles, recs = self.segment(k)
+        dec.detect_host(host_ptr, n_buffers, carry, recs, self.cap, tiles)
+        dec.publish_count(hdr)
+
     def fence(self):
         """All ranks: after this (stream-ordered) every rank's kernels up to here have completed."""
         return self.dist.all_reduce(self._flag, group=self.group, async_op=True)

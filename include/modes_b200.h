@@ -155,6 +155,10 @@ int  modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples,
  * NULL to use the context's own workspace. */
 int  modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, const uint8_t *carry476,
                          void *d_candidates, size_t cand_capacity, void *d_tiles);
+/* Same, from HOST memory (pinned for full speed): the library stages the buffers into its own device
+ * memory with one asynchronous copy on the same stream, then launches the kernels. */
+int  modes_detect_host(modes_ctx *ctx, const uint8_t *iq, size_t n_buffers, const uint8_t *carry476,
+                       void *d_candidates, size_t cand_capacity, void *d_tiles);
 /* Wait for the last modes_detect_device; returns the candidate count. */
 int  modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates);
 /* Copy the last result to host memory (arrays sized by the caller from
@@ -181,6 +185,7 @@ int  modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, co
 int  modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_candidate *const *candidates,
                                const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
                                modes_sink_fn sink, void *user);
+int  modes_resolver_reset(modes_resolver *r);           /* forget ICAO cache, skip state, statistics */
 int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
 int    modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity);   /* like modes_set_output */
 size_t modes_resolver_output_count(const modes_resolver *r);
