@@ -53,6 +53,12 @@ class Message(C.Structure):
         """The --raw output line, dump1090.c:1324-1326."""
         return "*" + self.hex() + ";"
 
+    def text(self, check_crc: int = 1) -> str:
+        """The reference's default (non --raw) output for this message, dump1090.c:1314-1450."""
+        buf = C.create_string_buffer(2048)
+        n = lib().modes_format_message(C.byref(self), int(check_crc), buf, 2048)
+        return buf.raw[:n].decode("latin1")
+
     def copy(self) -> "Message":
         m = Message()
         C.memmove(C.byref(m), C.byref(self), C.sizeof(Message))
@@ -94,7 +100,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_host", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
@@ -139,6 +145,8 @@ def lib():
         L.modes_resolver_output_count.restype = C.c_size_t
         L.modes_resolver_output_count.argtypes = [C.c_void_p]
         L.modes_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Message)]
+        L.modes_format_message.restype = C.c_size_t
+        L.modes_format_message.argtypes = [C.POINTER(Message), C.c_int, C.c_char_p, C.c_size_t]
         L.modes_stream.restype = C.c_void_p
         L.modes_stream.argtypes = [C.c_void_p]
         L.modes_set_stream.argtypes = [C.c_void_p, C.c_void_p]

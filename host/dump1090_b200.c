@@ -14,10 +14,10 @@
 #include <string.h>
 #include "modes_b200.h"
 
-static int opt_raw = 0, opt_onlyaddr = 0, opt_stats = 0;
+static int opt_raw = 0, opt_onlyaddr = 0, opt_stats = 0, opt_check_crc = 1;
 
 /* Message sink: the --raw / --onlyaddr forms of displayModesMessage
- * (dump1090.c:1318-1331) and the CRC line of the full form (:1333-1335). */
+ * (dump1090.c:1318-1331) and, by default, the full text (:1314-1450) via modes_format_message(). */
 static void on_message(void *user, const modes_message *mm) {
     (void)user;
     if (opt_stats) return;                                  /* dump1090.c:1803 */
@@ -25,14 +25,16 @@ static void on_message(void *user, const modes_message *mm) {
         printf("%02x%02x%02x\n", mm->aa1, mm->aa2, mm->aa3);
         return;
     }
+    if (!opt_raw) {                                         /* the full text, dump1090.c:1314-1450 */
+        char text[2048];
+        size_t n = modes_format_message(mm, opt_check_crc, text, sizeof(text));
+        fwrite(text, 1, n < sizeof(text) ? n : sizeof(text) - 1, stdout);
+        return;
+    }
     printf("*");
     for (int j = 0; j < mm->msgbits / 8; j++) printf("%02x", mm->msg[j]);
     printf(";\n");
     if (opt_raw) return;
-    printf("CRC: %06x (%s)\n", (int)mm->crc, mm->crcok ? "ok" : "wrong");
-    if (mm->errorbit != -1) printf("Single bit error fixed, bit %d\n", mm->errorbit);
-    printf("DF %d, ICAO %02x%02x%02x, sample %lld\n\n", mm->msgtype, mm->aa1, mm->aa2, mm->aa3,
-           (long long)mm->sample_pos);
 }
 
 int main(int argc, char **argv) {
@@ -46,7 +48,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[j], "--raw")) opt_raw = 1;
         else if (!strcmp(argv[j], "--onlyaddr")) opt_onlyaddr = 1;
         else if (!strcmp(argv[j], "--no-fix")) cfg.fix_errors = 0;
-        else if (!strcmp(argv[j], "--no-crc-check")) cfg.check_crc = 0;
+        else if (!strcmp(argv[j], "--no-crc-check")) { cfg.check_crc = 0; opt_check_crc = 0; }
         else if (!strcmp(argv[j], "--aggressive")) cfg.aggressive = 1;
         else if (!strcmp(argv[j], "--stats")) opt_stats = 1;
         else if (!strcmp(argv[j], "--drop-eof-buffer")) cfg.drop_eof_buffer = 1;

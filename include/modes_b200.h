@@ -195,6 +195,13 @@ size_t modes_resolver_output_count(const modes_resolver *r);
  * device + resolve path with the context's ICAO cache. */
 int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out);
 
+/* ---- presentation -------------------------------- */
+/* The reference's default (non --raw) text for one message: displayModesMessage()
+ * (dump1090.c:1314-1450) plus the blank line of useModesMessage() (:1813), byte for byte.
+ * check_crc = the --no-crc-check state (it changes one line, :1445).  Returns the length the text
+ * needs; at most capacity-1 bytes + NUL are written.  Pure host code. */
+size_t modes_format_message(const modes_message *mm, int check_crc, char *buf, size_t capacity);
+
 /* ---- plumbing ----------------------------------------------------------- */
 void *modes_stream(modes_ctx *ctx);                    /* the cudaStream_t modes_detect_device launches on */
 int   modes_set_stream(modes_ctx *ctx, void *cuda_stream);   /* use the caller's stream for it (NULL: own) */

@@ -111,6 +111,17 @@ def test_c_host_binary(checker_libs):
     for flags, (n, md5) in pins.items():
         out = subprocess.run([str(exe), "--ifile", f, "--raw", *flags], capture_output=True, check=True).stdout
         assert out.count(b"\n") == n and hashlib.md5(out).hexdigest().startswith(md5), flags
+    # default output = the full text of displayModesMessage (dump1090.c:1314-1450): byte-identical to the
+    # reference harness binary, which prints through the reference's own function
+    ref_bin = C.ORACLE_DIR / "_ref" / "ref_dump1090"
+    if ref_bin.exists():
+        for flags in ([], ["--aggressive", "--no-crc-check"]):
+            ours = subprocess.run([str(exe), "--ifile", f, *flags], capture_output=True, check=True).stdout
+            theirs = subprocess.run([str(ref_bin), "--ifile", f, *flags], capture_output=True, check=True).stdout
+            assert ours == theirs, flags
+        ours = subprocess.run([str(exe), "--ifile", f, "--onlyaddr"], capture_output=True, check=True).stdout
+        theirs = subprocess.run([str(ref_bin), "--ifile", f, "--onlyaddr"], capture_output=True, check=True).stdout
+        assert ours == theirs
     stats = subprocess.run([str(exe), "--ifile", f, "--stats"], capture_output=True, check=True, text=True).stdout
     assert stats.splitlines()[:4] == ["546 valid preambles", "282 demodulated again after phase correction",
                                       "535 demodulated with zero errors", "276 with good crc"]
