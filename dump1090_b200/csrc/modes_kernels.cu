@@ -26,6 +26,7 @@
 //    inside applyPhaseCorrection are both "last definite value wins" scans; on
 //    ballot words they are the carry chain of one 128-bit addition (fill128).
 #include <cstdint>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "modes_internal.h"
 
@@ -118,14 +119,23 @@ struct TileSrc {
     bool interior;
 };
 
+template <int kVariant>
 __device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
-    if (t.interior) return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+    if (t.interior) {
+        if (kVariant == 2) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+        return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+    }
     return load_vchunk(in, t.c0 + chunk, n_vchunks);
 }
 
-// Squared magnitude of tile sample s (0 .. 4096+23) from the warp's shared-memory copy.
-__device__ __forceinline__ uint32_t tile_n(const uint8_t *raw, int s) {
-    const uint32_t w = *reinterpret_cast<const uint16_t *>(raw + 2 * s);
+// Squared magnitude of tile sample s (0 .. 4096+23): from the warp's shared-memory copy of the
+// tile (variant 0) or re-read from global memory / L2.
+template <int kVariant>
+__device__ __forceinline__ uint32_t tile_n(const BatchView &in, const TileSrc &t, const uint8_t *raw, int s) {
+    uint32_t w;
+    if (kVariant == 0) w = *reinterpret_cast<const uint16_t *>(raw + 2 * s);
+    else if (t.interior) w = __ldg(reinterpret_cast<const uint16_t *>(t.flat) + s);
+    else return sample_n(in, t.c0 * 8 + s);
     const uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
     return __dp4a(a, a, 0u);
 }
@@ -134,10 +144,13 @@ __device__ __forceinline__ uint32_t tile_n(const uint8_t *raw, int s) {
 //   high = (m0+m2+m7+m9)/6;  m4, m5, m11..m14 < high
 // <=> 6*(max(m4,m5,m11..m14)+1) <= m0+m2+m7+m9, and the magnitude table is monotone in the
 // squared magnitude, so the max is taken before the lookup: five lookups instead of ten.
-__device__ __forceinline__ bool high_tests(const uint8_t *raw, int s, const uint16_t *__restrict__ lutn) {
-    const uint32_t n0 = tile_n(raw, s), n2 = tile_n(raw, s + 2), n7 = tile_n(raw, s + 7), n9 = tile_n(raw, s + 9);
-    const uint32_t n4 = tile_n(raw, s + 4), n5 = tile_n(raw, s + 5), n11 = tile_n(raw, s + 11);
-    const uint32_t n12 = tile_n(raw, s + 12), n13 = tile_n(raw, s + 13), n14 = tile_n(raw, s + 14);
+template <int kVariant>
+__device__ __forceinline__ bool high_tests(const BatchView &in, const TileSrc &t, const uint8_t *raw, int s,
+                                           const uint16_t *__restrict__ lutn) {
+#define TN(d) tile_n<kVariant>(in, t, raw, s + (d))
+    const uint32_t n0 = TN(0), n2 = TN(2), n7 = TN(7), n9 = TN(9);
+    const uint32_t n4 = TN(4), n5 = TN(5), n11 = TN(11), n12 = TN(12), n13 = TN(13), n14 = TN(14);
+#undef TN
     const uint32_t nx = max(max(max(n4, n5), max(n11, n12)), max(n13, n14));
     const int sum = (int)__ldg(lutn + n0) + (int)__ldg(lutn + n2) + (int)__ldg(lutn + n7) + (int)__ldg(lutn + n9);
     const int mx = __ldg(lutn + nx);
@@ -185,7 +198,7 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
         const int r = (r_);                                                                                        \
         uint32_t Pn[4];                                                                                            \
         Pn[0] = n2_pack15(xn.x); Pn[1] = n2_pack15(xn.y); Pn[2] = n2_pack15(xn.z); Pn[3] = n2_pack15(xn.w);        \
-        reinterpret_cast<uint4 *>(raw)[32 * (r + 1) + lane] = xn;                                                  \
+        if (kVariant == 0) reinterpret_cast<uint4 *>(raw)[32 * (r + 1) + lane] = xn;                               \
         uint32_t P[9];                                                                                             \
         P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];                                                    \
         _Pragma("unroll") for (int k = 0; k < 4; k++)                                                              \
@@ -219,13 +232,18 @@ __device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, 
     return ts;
 }
 
+// kVariant 0: the tile's raw bytes are kept in shared memory for the exact tests (DRAM traffic
+// = 1.00x the input, 19 warps/SM).  1 / 2: no copy, the exact tests re-read their samples from
+// global memory (L2), 32 warps/SM; 2 additionally lets the row loads allocate in L1.
+template <int kVariant>
 __global__ void __launch_bounds__(32)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
+    constexpr int kRaw = kVariant == 0 ? kRawBytes : 0;
     uint8_t *raw = smem;                                                             // tile's raw I/Q (17 rows), chunk order
-    uint8_t *rowmask = smem + kRawBytes;                                             // 512 flag bytes: byte = position/8
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + kRawBytes + 512);           // survivor positions
-    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + kRawBytes + 512 + kSurvivorCap * 2);  // 2 x candidate lists
+    uint8_t *rowmask = smem + kRaw;                                                  // 512 flag bytes: byte = position/8
+    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + kRaw + 512);                // survivor positions
+    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + kRaw + 512 + kSurvivorCap * 2);  // 2 x candidate lists
     uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
 
     const int lane = threadIdx.x;
@@ -236,8 +254,8 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
     uint32_t g = blockIdx.x;
     if (g >= n_tiles) return;
     TileSrc ts = tile_source(in, g, n_vchunks);
-    uint4 x0 = load_row_chunk(in, ts, lane, n_vchunks), x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
-    uint4 x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
+    uint4 x0 = load_row_chunk<kVariant>(in, ts, lane, n_vchunks), x1 = load_row_chunk<kVariant>(in, ts, 32 + lane, n_vchunks);
+    uint4 x2 = load_row_chunk<kVariant>(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk<kVariant>(in, ts, 96 + lane, n_vchunks);
 
     for (int it = 0; g < n_tiles; ++it) {
         const int cur = it & 1;
@@ -247,18 +265,18 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
         // a full group of arithmetic between issue and first use).
         uint32_t Pc[4];
         Pc[0] = n2_pack15(x0.x); Pc[1] = n2_pack15(x0.y); Pc[2] = n2_pack15(x0.z); Pc[3] = n2_pack15(x0.w);
-        reinterpret_cast<uint4 *>(raw)[lane] = x0;
+        if (kVariant == 0) reinterpret_cast<uint4 *>(raw)[lane] = x0;
 #pragma unroll 1
         for (int rr = 0; rr < 16; rr += 4) {
             const uint4 pad = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
             uint4 y0 = pad, y1 = pad, y2 = pad, y3 = pad;       // rows rr+4 .. rr+7
             if (rr + 4 < 16) {
-                y0 = load_row_chunk(in, ts, 32 * (rr + 4) + lane, n_vchunks);
-                y1 = load_row_chunk(in, ts, 32 * (rr + 5) + lane, n_vchunks);
-                y2 = load_row_chunk(in, ts, 32 * (rr + 6) + lane, n_vchunks);
-                y3 = load_row_chunk(in, ts, 32 * (rr + 7) + lane, n_vchunks);
+                y0 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 4) + lane, n_vchunks);
+                y1 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 5) + lane, n_vchunks);
+                y2 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 6) + lane, n_vchunks);
+                y3 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 7) + lane, n_vchunks);
             } else if (lane < 3) {
-                y0 = load_row_chunk(in, ts, 32 * 16 + lane, n_vchunks);   // the row after the tile: lookahead only
+                y0 = load_row_chunk<kVariant>(in, ts, 32 * 16 + lane, n_vchunks);   // the row after the tile: lookahead only
             }
             MODES_SCAN_ROW(rr + 0, x1)
             MODES_SCAN_ROW(rr + 1, x2)
@@ -269,10 +287,11 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
 
         // ---- start the next tile's first four rows now; they arrive while this tile is finished
         const uint32_t g_next = g + gridDim.x;
+        const TileSrc ts_cur = ts;
         if (g_next < n_tiles) {
             ts = tile_source(in, g_next, n_vchunks);
-            x0 = load_row_chunk(in, ts, lane, n_vchunks); x1 = load_row_chunk(in, ts, 32 + lane, n_vchunks);
-            x2 = load_row_chunk(in, ts, 64 + lane, n_vchunks); x3 = load_row_chunk(in, ts, 96 + lane, n_vchunks);
+            x0 = load_row_chunk<kVariant>(in, ts, lane, n_vchunks); x1 = load_row_chunk<kVariant>(in, ts, 32 + lane, n_vchunks);
+            x2 = load_row_chunk<kVariant>(in, ts, 64 + lane, n_vchunks); x3 = load_row_chunk<kVariant>(in, ts, 96 + lane, n_vchunks);
         }
         __syncwarp();
         // lane j now takes the 128 consecutive positions [128j, 128j+128) of the tile
@@ -322,7 +341,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
             for (uint32_t i0 = 0; i0 < n_surv; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 const int spos = i < n_surv ? surv[i] : 0;
-                const bool pass = i < n_surv && high_tests(raw, spos, lutn);
+                const bool pass = i < n_surv && high_tests<kVariant>(in, ts_cur, raw, spos, lutn);
                 const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                 const uint32_t slot = n_out + __popc(bal & ((1u << lane) - 1u));
                 if (pass && slot < (uint32_t)kOutCap) olist[slot] = (uint16_t)spos;
@@ -352,7 +371,7 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                     for (uint32_t i0 = 0; i0 < n_here; i0 += 32) {
                         const uint32_t i = i0 + lane;
                         const int spos = i < n_here ? surv[i] : 0;
-                        const bool pass = i < n_here && high_tests(raw, spos, lutn);
+                        const bool pass = i < n_here && high_tests<kVariant>(in, ts_cur, raw, spos, lutn);
                         const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                         if (pass_no == 1 && pass) {
                             const uint32_t idx = base + run + __popc(bal & ((1u << lane) - 1u));
@@ -379,19 +398,29 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
     if (pend_tile != 0xffffffffu) emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
 }
 
-void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
-                 cudaStream_t stream) {
+template <int kVariant>
+static void launch_scan_variant(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
+                                cudaStream_t stream) {
+    constexpr int smem = kScanWarpSmem - (kVariant == 0 ? 0 : kRawBytes);
     static int ctas_per_sm = 0;
     if (!ctas_per_sm) {
-        cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScanWarpSmem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel, 32, kScanWarpSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(scan_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<kVariant>, 32, smem) != cudaSuccess ||
             ctas_per_sm < 1)
             ctas_per_sm = 16;
     }
     const uint32_t n_tiles = tiles_for(in.n_samples);
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);  // persistent single-warp CTAs, all resident
     if (grid > n_tiles) grid = n_tiles;
-    scan_kernel<<<grid, 32, kScanWarpSmem, stream>>>(in, tab.lutn, out, n_tiles);
+    scan_kernel<kVariant><<<grid, 32, smem, stream>>>(in, tab.lutn, out, n_tiles);
+}
+
+void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
+                 cudaStream_t stream) {
+    static const int variant = [] { const char *e = getenv("MODES_SCAN_VARIANT"); return e ? atoi(e) : 0; }();
+    if (variant == 1) launch_scan_variant<1>(in, tab, out, sm_count, stream);
+    else if (variant == 2) launch_scan_variant<2>(in, tab, out, sm_count, stream);
+    else launch_scan_variant<0>(in, tab, out, sm_count, stream);
 }
 
 // ------------------------------------------------------- K2: frame evaluation
