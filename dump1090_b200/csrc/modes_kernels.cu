@@ -122,7 +122,7 @@ struct TileSrc {
 template <int kVariant>
 __device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
     if (t.interior) {
-        if (kVariant == 2) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+        if (kVariant >= 2) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
         return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
     }
     return load_vchunk(in, t.c0 + chunk, n_vchunks);
@@ -236,7 +236,7 @@ __device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, 
 // = 1.00x the input, 19 warps/SM).  1 / 2: no copy, the exact tests re-read their samples from
 // global memory (L2), 32 warps/SM; 2 additionally lets the row loads allocate in L1.
 template <int kVariant>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, kVariant == 3 ? 32 : (kVariant == 0 ? 20 : 28))
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int kRaw = kVariant == 0 ? kRawBytes : 0;
@@ -420,6 +420,7 @@ void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs
     static const int variant = [] { const char *e = getenv("MODES_SCAN_VARIANT"); return e ? atoi(e) : 0; }();
     if (variant == 1) launch_scan_variant<1>(in, tab, out, sm_count, stream);
     else if (variant == 2) launch_scan_variant<2>(in, tab, out, sm_count, stream);
+    else if (variant == 3) launch_scan_variant<3>(in, tab, out, sm_count, stream);
     else launch_scan_variant<0>(in, tab, out, sm_count, stream);
 }
 
