@@ -122,7 +122,8 @@ struct TileSrc {
 template <int kVariant>
 __device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
     if (t.interior) {
-        if (kVariant >= 2) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
+        // variant 1 lets the row allocate in L1: the exact tests re-read a few of its samples
+        if (kVariant == 1) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
         return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
     }
     return load_vchunk(in, t.c0 + chunk, n_vchunks);
@@ -232,11 +233,12 @@ __device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, 
     return ts;
 }
 
-// kVariant 0: the tile's raw bytes are kept in shared memory for the exact tests (DRAM traffic
-// = 1.00x the input, 19 warps/SM).  1 / 2: no copy, the exact tests re-read their samples from
-// global memory (L2), 32 warps/SM; 2 additionally lets the row loads allocate in L1.
+// kVariant 1 (default): nothing is staged; the rows are loaded through L1 and the exact tests
+// re-read their few samples from it (measured DRAM traffic 1.015x the input), 64 registers and
+// 2.5 KB of shared memory per warp -> 32 warps/SM.  kVariant 0 keeps a copy of the tile's raw bytes
+// in shared memory instead (traffic 1.00x, 19 warps/SM, ~10 % slower); MODES_SCAN_VARIANT=0 selects it.
 template <int kVariant>
-__global__ void __launch_bounds__(32, kVariant == 3 ? 32 : (kVariant == 0 ? 20 : 28))
+__global__ void __launch_bounds__(32, kVariant == 1 ? 32 : 19)
 scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr int kRaw = kVariant == 0 ? kRawBytes : 0;
@@ -417,11 +419,9 @@ static void launch_scan_variant(const BatchView &in, const DeviceTables &tab, co
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream) {
-    static const int variant = [] { const char *e = getenv("MODES_SCAN_VARIANT"); return e ? atoi(e) : 0; }();
-    if (variant == 1) launch_scan_variant<1>(in, tab, out, sm_count, stream);
-    else if (variant == 2) launch_scan_variant<2>(in, tab, out, sm_count, stream);
-    else if (variant == 3) launch_scan_variant<3>(in, tab, out, sm_count, stream);
-    else launch_scan_variant<0>(in, tab, out, sm_count, stream);
+    static const int variant = [] { const char *e = getenv("MODES_SCAN_VARIANT"); return e ? atoi(e) : 1; }();
+    if (variant == 0) launch_scan_variant<0>(in, tab, out, sm_count, stream);
+    else launch_scan_variant<1>(in, tab, out, sm_count, stream);
 }
 
 // ------------------------------------------------------- K2: frame evaluation
