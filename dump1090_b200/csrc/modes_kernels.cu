@@ -50,19 +50,6 @@ __device__ __forceinline__ uint4 load_vchunk(const BatchView &in, uint64_t c, ui
     return ldg_stream(p);
 }
 
-// Two I/Q pairs (bytes I0 Q0 I1 Q1) -> two squared magnitudes packed as u16x2.
-// |b-127| per byte in one SIMD instruction, then a byte dot product each.
-__device__ __forceinline__ uint32_t iq2_to_n2(uint32_t w) {
-    uint32_t a = __vabsdiffu4(w, 0x7f7f7f7fu);
-    uint32_t n0 = __dp4a(a & 0x0000ffffu, a, 0u);
-    uint32_t n1 = __dp4a(a & 0xffff0000u, a, 0u);
-    return n0 | (n1 << 16);
-}
-
-__device__ __forceinline__ uint4 iq8_to_n8(uint4 raw) {
-    return make_uint4(iq2_to_n2(raw.x), iq2_to_n2(raw.y), iq2_to_n2(raw.z), iq2_to_n2(raw.w));
-}
-
 // One sample of the virtual array -> squared magnitude.
 __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
     const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);

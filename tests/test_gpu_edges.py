@@ -207,3 +207,16 @@ def test_caller_buffers_overflow_is_reported(gpu_decoder_factory):
     dec.detect_device(d.data_ptr(), 1, None, small.data_ptr(), 100, tiles.data_ptr())
     with pytest.raises(RuntimeError, match="capacity exceeded"):
         dec.detect_wait()
+
+
+def test_two_gpu_fused_gather(checker_libs):
+    """With two or more GPUs on the box: the sharded decode with the record gather fused into the
+    kernels (CUDA-IPC peer stores into rank 0's HBM) equals the oracle (scripts/multi_gpu_parity.py)."""
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(ROOT / "scripts" / "multi_gpu_parity.py")],
+                         capture_output=True, text=True, cwd=str(ROOT), timeout=600)
+    assert "MULTI_GPU_PARITY PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
