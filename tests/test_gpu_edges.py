@@ -220,3 +220,19 @@ def test_two_gpu_fused_gather(checker_libs):
                           "--master-addr", "127.0.0.1", "--master-port", "29577", str(ROOT / "scripts" / "multi_gpu_parity.py")],
                          capture_output=True, text=True, cwd=str(ROOT), timeout=600)
     assert "MULTI_GPU_PARITY PASS" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("snr_db", [0, 6, 10, 15])
+def test_low_snr_detect_rate_identical(snr_db, gpu_decoder_factory, checker_libs):
+    """BASELINE.json configs[4] in miniature: injected DF17 at low SNR, --aggressive; the GPU must make
+    exactly the oracle's decisions (same messages, same repairs), not merely a similar detect rate."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("snr_sweep", ROOT / "scripts" / "snr_sweep.py")
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)
+    data, truth = sweep.stream_at(float(snr_db), 400, 2000 + snr_db)
+    exp, st = C.oracle_decode(data, aggressive=1, cap=8192)
+    dec = gpu_decoder_factory(aggressive=1)
+    got = dec.decode(data)
+    assert [C.msg_fields(m) for m in got] == [C.msg_fields(m) for m in exp]
+    assert list(dec.stats().values()) == st
