@@ -534,9 +534,15 @@ __device__ __forceinline__ void frame_words(U128 F, uint32_t W[4]) {
 
 // Slice 112 bits from (lo, hi) half-bit magnitudes held 4 rounds per lane
 // (round r, lane l <-> bit 32r+l), then gate, CRC, repair.
+// `sliced` carries the frame bits as sliced (before any repair) and the tri-state flag; when
+// `prev`/`prev_sliced` describe an earlier attempt that sliced the very same bits (the phase
+// correction often changes no decision), its gate / CRC / repair results are reused.
+struct Sliced { U128 F; uint32_t tri; };
+
 __device__ __forceinline__ void evaluate_pass(const int lo[4], const int hi[4], uint32_t sum56, uint32_t sum112,
                                               int fix_errors, int aggressive, const uint32_t *s_syn,
-                                              const uint32_t *s_hash, int lane, PassResult &R) {
+                                              const uint32_t *s_hash, int lane, PassResult &R, Sliced &sliced,
+                                              const PassResult *prev = nullptr, const Sliced *prev_sliced = nullptr) {
     bool def[4], one[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
@@ -561,6 +567,12 @@ __device__ __forceinline__ void evaluate_pass(const int lo[4], const int hi[4], 
         F.hi |= e1 & 0x7f7f7f7f7f7f7f7full;
     }
     F.hi &= 0x0000ffffffffffffull;
+    sliced.F = F; sliced.tri = tri;
+    if (prev && prev_sliced->F.lo == F.lo && prev_sliced->F.hi == F.hi && prev_sliced->tri == tri) {
+        R = *prev;                                       // same bits, same (uncorrected) delta sums: same verdict
+        R.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
+        return;
+    }
     uint32_t W0 = __brev((uint32_t)F.lo);
     R.msgtype = W0 >> 27;
     const int msgbits = (R.msgtype >= 16 && R.msgtype <= 21) ? 112 : 56;      // dump1090.c:746-753
@@ -694,7 +706,8 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
         d112 = __reduce_add_sync(0xffffffffu, d112);
 
         PassResult P1, P2;
-        evaluate_pass(lo, hi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P1);
+        Sliced S1, S2;
+        evaluate_pass(lo, hi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P1, S1);
         P2.W[0] = P2.W[1] = P2.W[2] = P2.W[3] = 0;
         P2.msgtype = 0; P2.flags = 0; P2.errorbit = 0; P2.nfixed = 0; P2.crc = 0;
 
@@ -764,7 +777,7 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
                         else if (b < 112) clo[r] = bit_of(E, b - 1) ? lu[r] : ld[r];
                     }
                 }
-                evaluate_pass(clo, chi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P2);
+                evaluate_pass(clo, chi, d56, d112, fix_errors, aggressive, s_syn, s_hash, lane, P2, S2, &P1, &S1);
             }
         }
 
