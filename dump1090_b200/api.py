@@ -59,6 +59,12 @@ class Message(C.Structure):
         n = lib().modes_format_message(C.byref(self), int(check_crc), buf, 2048)
         return buf.raw[:n].decode("latin1")
 
+    def raw_net_line(self) -> str:
+        """The TCP raw-output line (uppercase hex), dump1090.c:2381-2393."""
+        buf = C.create_string_buffer(64)
+        n = lib().modes_format_raw_net(C.byref(self), buf, 64)
+        return buf.raw[:n].decode("latin1")
+
     def copy(self) -> "Message":
         m = Message()
         C.memmove(C.byref(m), C.byref(self), C.sizeof(Message))
@@ -100,7 +106,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_host", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_format_raw_net", "modes_parse_hex_line", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
@@ -147,6 +153,9 @@ def lib():
         L.modes_decode_frame.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Message)]
         L.modes_format_message.restype = C.c_size_t
         L.modes_format_message.argtypes = [C.POINTER(Message), C.c_int, C.c_char_p, C.c_size_t]
+        L.modes_format_raw_net.restype = C.c_size_t
+        L.modes_format_raw_net.argtypes = [C.POINTER(Message), C.c_char_p, C.c_size_t]
+        L.modes_parse_hex_line.argtypes = [C.c_char_p, C.c_void_p]
         L.modes_stream.restype = C.c_void_p
         L.modes_stream.argtypes = [C.c_void_p]
         L.modes_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -171,6 +180,15 @@ def lib():
         L.modes_launch_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
+
+
+def parse_hex_line(line: str | bytes):
+    """decodeHexMessage's parser (dump1090.c:2472-2497): frame bytes, or None if the line is discarded."""
+    if isinstance(line, str):
+        line = line.encode("latin1")
+    msg = (C.c_uint8 * 14)()
+    n = lib().modes_parse_hex_line(line, msg)
+    return None if n < 0 else bytes(msg)
 
 
 def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, device=0, profile=0,

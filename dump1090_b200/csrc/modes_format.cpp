@@ -156,3 +156,42 @@ extern "C" size_t modes_format_message(const modes_message *mm, int check_crc, c
     o.put("\n");
     return o.len;
 }
+
+// The raw TCP output line (port 30002), modesSendRawOutput dump1090.c:2381-2393: "*" + UPPERCASE
+// hex + ";\n" (the stdout form of :1324-1326 is lowercase).
+extern "C" size_t modes_format_raw_net(const modes_message *mm, char *buf, size_t capacity) {
+    Out o{buf, capacity, 0};
+    o.put("*");
+    for (int j = 0; j < mm->msgbits / 8; j++) o.put("%02X", mm->msg[j]);
+    o.put(";\n");
+    return o.len;
+}
+
+// The raw TCP input line (port 30001), the parsing half of decodeHexMessage dump1090.c:2472-2497:
+// surrounding white space ignored, "*" ... ";" required, at most 28 hex digits, any non-hex digit
+// (or an odd digit count, which makes the reference pair a digit with ';') discards the line.
+// Returns the number of frame bytes written (0..14) or -1 if the reference discards the line.
+// Bytes the line does not supply are zeroed (the reference leaves them uninitialised).
+extern "C" int modes_parse_hex_line(const char *line, uint8_t msg[14]) {
+    auto is_space = [](unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); };
+    auto hexval = [](unsigned char c) -> int {
+        if (c >= '0' && c <= '9') return c - '0';
+        c |= 0x20;
+        if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+        return -1;
+    };
+    std::memset(msg, 0, 14);
+    size_t l = std::strlen(line);
+    while (l && is_space((unsigned char)line[l - 1])) l--;
+    while (l && is_space((unsigned char)*line)) { line++; l--; }
+    if (l < 2 || line[0] != '*' || line[l - 1] != ';') return -1;
+    line++; l -= 2;
+    if (l > 28) return -1;
+    for (size_t j = 0; j < l; j += 2) {
+        const int hi = hexval((unsigned char)line[j]);
+        const int lo = j + 1 < l ? hexval((unsigned char)line[j + 1]) : -1;
+        if (hi < 0 || lo < 0) return -1;
+        msg[j / 2] = (uint8_t)((hi << 4) | lo);
+    }
+    return (int)(l / 2);
+}

@@ -202,6 +202,14 @@ int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *ou
  * needs; at most capacity-1 bytes + NUL are written.  Pure host code. */
 size_t modes_format_message(const modes_message *mm, int check_crc, char *buf, size_t capacity);
 
+/* SURVEY.md §8(f) item 2 — the raw TCP wire formats.  Output line of port 30002
+ * (modesSendRawOutput, dump1090.c:2381-2393): "*" + UPPERCASE hex + ";\n". */
+size_t modes_format_raw_net(const modes_message *mm, char *buf, size_t capacity);
+/* Input line of port 30001, the parsing half of decodeHexMessage (dump1090.c:2472-2497).  Returns
+ * the number of frame bytes written to msg (0..14; the rest zeroed) or -1 where the reference
+ * discards the line.  Feed the bytes to modes_decode_frame() for the decoding half. */
+int    modes_parse_hex_line(const char *line, uint8_t msg[14]);
+
 /* ---- plumbing ----------------------------------------------------------- */
 void *modes_stream(modes_ctx *ctx);                    /* the cudaStream_t modes_detect_device launches on */
 int   modes_set_stream(modes_ctx *ctx, void *cuda_stream);   /* use the caller's stream for it (NULL: own) */

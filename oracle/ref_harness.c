@@ -186,6 +186,20 @@ void ref_decode_bytes(const unsigned char *msg14, int fix_errors, int aggressive
     copy_fields(out, &mm);
 }
 
+/* ctypes entry: the reference's own raw-TCP input handler (decodeHexMessage, dump1090.c:2472)
+ * on one text line, fresh ICAO cache.  Returns 1 and fills *out if it delivered a message
+ * (check_crc off, so every parsed line delivers), 0 if it discarded the line. */
+int ref_decode_hex_line(const char *line, int fix_errors, int aggressive, struct oracle_msg *out) {
+    static struct client c;
+    ref_reset(fix_errors, aggressive, 0, 0);
+    memset(&c, 0, sizeof(c));
+    strncpy(c.buf, line, MODES_CLIENT_BUF_SIZE);
+    g_out = out; g_out_cap = 1; g_out_n = 0; g_print = 0;
+    decodeHexMessage(&c);
+    g_out = NULL;
+    return g_out_n > 0;
+}
+
 #ifdef REF_HARNESS_MAIN
 /* CLI: ref_dump1090 --ifile F [--raw] [--no-fix] [--aggressive] [--no-crc-check]
  *                   [--stats] [--onlyaddr] [--drop-eof-buffer] [--time LOOPS] */

@@ -55,3 +55,33 @@ def test_text_buffer_too_small_is_safe():
     buf = ctypes.create_string_buffer(8)
     n = api.lib().modes_format_message(ctypes.byref(m), 1, buf, 8)
     assert n > 8 and buf.raw[7:8] == b"\0"
+
+
+def test_raw_net_line_is_uppercase():
+    m = api.Message()
+    m.msgbits = 56
+    for k, b in enumerate(bytes.fromhex("5d4840d6abcdef")):
+        m.msg[k] = b
+    assert m.raw_net_line() == "*5D4840D6ABCDEF;\n"          # dump1090.c:2387 "%02X"
+    assert m.raw_line() == "*5d4840d6abcdef;"               # dump1090.c:1325 "%02x"
+
+
+@needs_ref_bin
+def test_hex_line_parser_matches_reference(checker_libs):
+    """modes_parse_hex_line accepts / discards exactly the lines decodeHexMessage does, and yields the
+    frame bytes it decodes (full-length frames: the reference leaves missing bytes uninitialised)."""
+    import ctypes
+    ref = C.ref_lib()
+    full = "8D4B969699155600E87406F5B69F"
+    short = "5D4840D6ABCDEF"
+    lines = [f"*{full};", f"  *{full};\r\n", f"*{full.lower()};", f"*{short};", f"\t*{short};  ", f"*{full}", f"{full};",
+             f"*{full}00;", f"*{full[:-1]};", f"*{full[:-2]}zz;", "*;x", "", "   ", "*", ";", f"* {full};", f"*{full} ;"]
+    for line in lines:
+        out = C.Msg()
+        delivered = ref.ref_decode_hex_line(line.encode(), 1, 0, ctypes.byref(out))
+        got = api.parse_hex_line(line)
+        assert (got is not None) == bool(delivered), repr(line)
+        if got is not None and len(line.strip()) - 2 in (14, 28):
+            nbytes = out.msgbits // 8
+            if nbytes * 2 == len(line.strip()) - 2:          # DF length matches what the line supplied
+                assert got[:nbytes] == bytes(out.msg[:nbytes]), repr(line)
