@@ -440,13 +440,15 @@ int modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples, 
     CK(ctx, cudaSetDevice(ctx->cfg.device));
     uint8_t *d_iq = nullptr; uint16_t *d_mag = nullptr;
     cudaStream_t st = ctx->detect.stream;
-    CK(ctx, cudaMalloc(&d_iq, nsamples * 2));
-    if (cudaMalloc(&d_mag, nsamples * 2) != cudaSuccess) { cudaFree(d_iq); return fail(ctx, "cudaMalloc failed"); }
-    cudaMemcpyAsync(d_iq, iq, nsamples * 2, cudaMemcpyHostToDevice, st);
-    launch_magnitude(d_iq, d_mag, nsamples, ctx->d_lutn, st);
-    ctx->launches++;
-    cudaMemcpyAsync(mag, d_mag, nsamples * 2, cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
+    cudaError_t e = cudaMalloc(&d_iq, nsamples * 2);
+    if (e == cudaSuccess) e = cudaMalloc(&d_mag, nsamples * 2);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_iq, iq, nsamples * 2, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        launch_magnitude(d_iq, d_mag, nsamples, ctx->d_lutn, st);
+        ctx->launches++;
+        e = cudaMemcpyAsync(mag, d_mag, nsamples * 2, cudaMemcpyDeviceToHost, st);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cudaFree(d_iq); cudaFree(d_mag);
     if (e != cudaSuccess) return fail(ctx, "magnitude kernel failed: %s", cudaGetErrorString(e));
     return 0;

@@ -16,6 +16,11 @@
  *
  * There is no CPU fallback: modes_create() fails (NULL + modes_last_error)
  * when no CUDA device is usable.
+ *
+ * Threading: a context is not re-entrant (one thread at a time per modes_ctx, like the
+ * reference's single decode thread); distinct contexts are independent.  Callbacks run on the
+ * calling thread.  Status codes: 0 = ok, <0 = error with text in modes_last_error(ctx); the
+ * library never calls exit().
  */
 #ifndef MODES_B200_H
 #define MODES_B200_H
