@@ -246,6 +246,11 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
     uint4 x0 = load_row_chunk<kVariant>(in, ts, lane, n_vchunks), x1 = load_row_chunk<kVariant>(in, ts, 32 + lane, n_vchunks);
     uint4 x2 = load_row_chunk<kVariant>(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk<kVariant>(in, ts, 96 + lane, n_vchunks);
 
+    // Tiles are handed out dynamically (first come, first served from a global counter, after one
+    // static tile per warp): warps finish within a tile of each other instead of a stride's worth.
+    // The next index is requested a whole tile ahead, so the atomic's latency is never waited for.
+    uint32_t g_ahead = 0;
+    if (lane == 0) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
     for (int it = 0; g < n_tiles; ++it) {
         const int cur = it & 1;
 
@@ -275,7 +280,8 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
         }
 
         // ---- start the next tile's first four rows now; they arrive while this tile is finished
-        const uint32_t g_next = g + gridDim.x;
+        const uint32_t g_next = __shfl_sync(0xffffffffu, g_ahead, 0);
+        if (lane == 0 && g_next < n_tiles) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
         const TileSrc ts_cur = ts;
         if (g_next < n_tiles) {
             ts = tile_source(in, g_next, n_vchunks);
