@@ -44,7 +44,7 @@ struct ScanOutputs {
     uint32_t   *cand_v;          // virtual positions of candidates, tile by tile
     uint32_t    cand_capacity;
     modes_tile *tiles;           // [n_tiles]
-    uint32_t   *counters;        // [0] candidates found (may exceed capacity), [1] overflow flag
+    uint32_t   *counters;        // [0] candidates found (may exceed capacity), [1] overflow flag, [2]/[3] scan tile / eval chunk hand-out
 };
 
 inline uint32_t tiles_for(uint64_t n_samples) {

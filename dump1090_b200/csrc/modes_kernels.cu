@@ -630,8 +630,10 @@ __device__ __forceinline__ void load_window(const BatchView &in, uint32_t v, int
     }
 }
 
+constexpr uint32_t kEvalChunk = 8;
+
 __global__ void __launch_bounds__(kEvalThreads)
-eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, const uint32_t *counters,
+eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
             uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
     __shared__ uint32_t s_syn[112];
     __shared__ uint32_t s_hash[kFixHashSlots];
@@ -645,22 +647,31 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
     uint32_t n_cand = counters[0];
     if (n_cand > cand_capacity) n_cand = cand_capacity;
 
-    // Software pipeline: the raw words of the next candidate are requested before this one is
-    // evaluated, so the HBM round trip (cand_v -> I/Q words) overlaps a full evaluation.
-    const uint32_t stride = gridDim.x * warps_per_block;
-    uint32_t ci = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    // Candidates are handed out in chunks of kEvalChunk from a global counter (counters[3]), the
+    // next chunk requested while the current one is evaluated: evaluation cost varies by candidate
+    // (second pass or not, fix or not), so a static split leaves warps idle at the tail.
+    // Software pipeline across the chunk sequence: the raw words of the next candidate are
+    // requested before this one is evaluated, so the HBM round trip (cand_v -> I/Q words)
+    // overlaps a full evaluation; positions are fetched two candidates ahead.
+    const uint32_t total_warps = gridDim.x * warps_per_block;
+    uint32_t ci = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * kEvalChunk;   // chunk bases are multiples of kEvalChunk
+    uint32_t pending = 0;                                 // lane 0: chunk requested ahead
+    if (lane == 0) pending = total_warps + atomicAdd(&counters[3], 1u);
     RawWindow cur;
-    uint32_t v1 = 0;                                      // position of candidate ci + stride
+    uint32_t v1 = 0;                                      // position of the candidate after ci
     if (ci < n_cand) load_window(in, cand_v[ci], lane, cur);
-    if (ci + stride < n_cand) v1 = cand_v[ci + stride];
-    for (; ci < n_cand; ci += stride) {
-        // two dependent HBM round trips (position, then samples) are both kept off the critical
-        // path: positions are fetched two candidates ahead, sample words one candidate ahead
+    if (ci + 1 < n_cand) v1 = cand_v[ci + 1];
+    while (ci < n_cand) {
+        const uint32_t pos = ci & (kEvalChunk - 1);
+        uint32_t next_base = 0;                           // needed for the last two of a chunk only
+        if (pos >= kEvalChunk - 2) next_base = __shfl_sync(0xffffffffu, pending, 0) * kEvalChunk;
+        const uint32_t i1 = pos + 1 < kEvalChunk ? ci + 1 : next_base + (pos + 1 - kEvalChunk);
+        const uint32_t i2 = pos + 2 < kEvalChunk ? ci + 2 : next_base + (pos + 2 - kEvalChunk);
         RawWindow nxt;
         nxt.v = 0;
-        if (ci + stride < n_cand) load_window(in, v1, lane, nxt);
+        if (i1 < n_cand) load_window(in, v1, lane, nxt);
         uint32_t v2 = 0;
-        if (ci + 2 * stride < n_cand) v2 = cand_v[ci + 2 * stride];
+        if (i2 < n_cand) v2 = cand_v[i2];
 
         const uint32_t v = cur.v;
         const uint64_t t = (uint64_t)v - 2;
@@ -804,6 +815,10 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
         __syncwarp();
         cur = nxt;
         v1 = v2;
+        if (((++ci) & (kEvalChunk - 1)) == 0) {
+            ci = next_base;
+            if (lane == 0 && ci < n_cand) pending = total_warps + atomicAdd(&counters[3], 1u);
+        }
     }
 }
 
