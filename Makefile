@@ -11,7 +11,7 @@ OBJS      := build/modes_kernels.o build/modes_api.o build/modes_resolve.o build
 
 all: $(LIB) dump1090-b200
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/modes_internal.h include/modes_b200.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/modes_internal.h $(CSRC)/modes_eval_serial.cuh include/modes_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@
 
@@ -29,7 +29,14 @@ oracle:
 	$(MAKE) -C oracle
 	if [ -d /root/reference ]; then $(MAKE) -C oracle ref; fi
 
-clean:
-	rm -rf build $(LIB) dump1090-b200
+# test infrastructure: host build of the per-candidate evaluation (logic checked against the oracle on CPU)
+shim: tests/_build/libeval_serial_host.so
+tests/_build/libeval_serial_host.so: tests/host_shim/eval_serial_host.cpp $(CSRC)/modes_eval_serial.cuh $(CSRC)/modes_tables.cpp include/modes_b200.h
+	@mkdir -p tests/_build
+	g++ -O2 -std=c++17 -shared -fPIC -Wall -Wno-unknown-pragmas -x c++ -Iinclude -I$(CSRC) -I/usr/local/cuda/include \
+	    tests/host_shim/eval_serial_host.cpp $(CSRC)/modes_tables.cpp -o $@
 
-.PHONY: all oracle clean
+clean:
+	rm -rf build tests/_build $(LIB) dump1090-b200
+
+.PHONY: all oracle shim clean

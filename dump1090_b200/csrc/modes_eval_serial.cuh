@@ -1,0 +1,348 @@
+// modes_eval_serial.cuh — evaluation of ONE preamble candidate by ONE thread.
+//
+// This is the body of detectModeS after the preamble test (dump1090.c:1653-1735: bit slicing, delta
+// gate, the phase-corrected retry of :1498-1558) and the order-independent half of
+// decodeModesMessage (:1099-1128: CRC syndrome, single/two-bit repair), written as straight
+// sequential code over the candidate's 241-sample window.  eval_serial_kernel (modes_kernels.cu)
+// runs it with lane = candidate, the 32 windows of a warp staged in shared memory.
+//
+// The file has no CUDA dependencies besides a few integer intrinsics, so the test suite also
+// compiles it for the host (tests/host_shim/) and checks the logic against the oracle without a
+// GPU.  That build is test infrastructure; the product library contains only the device code.
+#pragma once
+#include <cstdint>
+#include "modes_b200.h"
+
+#if defined(__CUDACC__)
+#define MODES_SERIAL_FN __device__ __forceinline__
+#else
+#define MODES_SERIAL_FN static inline
+#endif
+
+namespace modes {
+namespace serial {
+
+// ---- the intrinsics ----------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+MODES_SERIAL_FN uint32_t absdiff127x4(uint32_t w) { return __vabsdiffu4(w, 0x7f7f7f7fu); }
+MODES_SERIAL_FN uint32_t dot4(uint32_t a, uint32_t b) { return __dp4a(a, b, 0u); }
+MODES_SERIAL_FN uint32_t bitrev(uint32_t x) { return __brev(x); }
+// (hi:lo) >> s for s in {16, 32}
+MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
+MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return __byte_perm(x, 0u, 0x0123u); }
+MODES_SERIAL_FN uint32_t ld_ro(const uint16_t *p) { return __ldg(p); }
+#else
+MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24); }
+MODES_SERIAL_FN uint32_t ld_ro(const uint16_t *p) { return *p; }
+MODES_SERIAL_FN uint32_t absdiff127x4(uint32_t w) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) {
+        int b = (int)((w >> (8 * k)) & 0xff) - 127;
+        r |= (uint32_t)(b < 0 ? -b : b) << (8 * k);
+    }
+    return r;
+}
+MODES_SERIAL_FN uint32_t dot4(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r += ((a >> (8 * k)) & 0xff) * ((b >> (8 * k)) & 0xff);
+    return r;
+}
+MODES_SERIAL_FN uint32_t bitrev(uint32_t x) {
+    uint32_t r = 0;
+    for (int k = 0; k < 32; k++) r |= ((x >> k) & 1u) << (31 - k);
+    return r;
+}
+MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) {
+    return s >= 32 ? hi : (uint32_t)((((uint64_t)hi << 32) | lo) >> s);
+}
+#endif
+
+// ---- window layout ----------------------------------------------------------------------------
+// A candidate at virtual position v owns the samples m[-1..239] = virtual samples v-1 .. v+239.
+// They are staged as kWindowWords aligned 32-bit words (two samples each); `odd` says whether
+// m[-1] is the high half of word 0.  Window sample w (w = 0 is m[-1]) is halfword w + odd.
+// Bit b of the frame is the sample pair (m[16+2b], m[17+2b]) = window samples 17+2b, 18+2b, i.e.
+// halfwords of words 8+b and 9+b.  After the first pass word 8+b holds the pair's magnitudes
+// (first | second << 16) instead; words 0..7 keep the raw preamble samples.
+constexpr int kWindowWords = 121;
+
+struct Tables {
+    const uint16_t *lutn;        // [32769] magnitude by i*i+q*q (dump1090.c:362)
+    const uint32_t *bit_syn;     // [112]   syndrome of one flipped bit
+    const uint32_t *byte_syn;    // [14*256] syndrome of byte value x at frame byte i: XOR of bit_syn over its set bits
+    const uint32_t *fix_hash;    // [256]   inverse of bit_syn over positions 5..111
+};
+
+// What one attempt (uncorrected, or phase corrected) yields: the six 32-bit words of a
+// modes_frame_eval (include/modes_b200.h) are made from it by eval_words().
+struct Verdict {
+    uint32_t F[4];               // frame bits, bit b of the frame at bit b (LSB first); after repair
+    uint32_t msgtype, flags, errorbit, nfixed, crc;
+};
+
+// Entry (pos, value) of Tables::byte_syn from the bit syndromes: bit 7-k of the byte is frame bit 8*pos+k.
+MODES_SERIAL_FN uint32_t byte_syndrome(const uint32_t *bit_syn, int pos, uint32_t value) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) x ^= ((value >> (7 - k)) & 1u) ? bit_syn[8 * pos + k] : 0u;
+    return x;
+}
+
+MODES_SERIAL_FN uint32_t fix_hash_of(uint32_t s) { return (s * 0x9E3779B1u) >> 24; }
+
+// Position (5..111) whose single-bit syndrome is s, or -1.
+MODES_SERIAL_FN int syndrome_pos(const uint32_t *fix_hash, uint32_t s) {
+    uint32_t h = fix_hash_of(s);
+    for (int i = 0; i < 256; i++) {
+        uint32_t e = fix_hash[(h + i) & 255u];
+        if (e == 0xFFFFFFFFu) return -1;
+        if ((e >> 8) == s) return (int)(e & 0xff);
+    }
+    return -1;
+}
+
+MODES_SERIAL_FN void flip_bit(uint32_t F[4], int b) {
+    // no dynamic register indexing: four predicated XORs
+    const uint32_t m = 1u << (b & 31);
+    const int w = b >> 5;
+    F[0] ^= (w == 0) ? m : 0u; F[1] ^= (w == 1) ? m : 0u;
+    F[2] ^= (w == 2) ? m : 0u; F[3] ^= (w == 3) ? m : 0u;
+}
+
+// Frame byte i (0..13) of F: bit 8i is its most significant bit.
+MODES_SERIAL_FN uint32_t frame_byte(const uint32_t W[4], int i) {        // W = bit-reversed F words
+    const uint32_t w = (i < 4) ? W[0] : (i < 8) ? W[1] : (i < 12) ? W[2] : W[3];
+    return (w >> (24 - 8 * (i & 3))) & 0xffu;
+}
+
+// CRC syndrome of the first msgbits of F, then the repairs of dump1090.c:1114-1126 (:733-742
+// checksum, :854-894 fixes).  F is modified by a repair.
+MODES_SERIAL_FN void crc_and_fix(uint32_t F[4], int msgbits, uint32_t msgtype, int fix_errors, int aggressive,
+                                 const Tables &tab, uint32_t &crc, uint32_t &errorbit, uint32_t &nfixed) {
+    const int off = 112 - msgbits;                      // a short frame uses the last 56 table positions
+    const uint32_t W[4] = {bitrev(F[0]), bitrev(F[1]), bitrev(F[2]), bitrev(F[3])};
+    uint32_t S = 0;
+#pragma unroll
+    for (int i = 0; i < 14; i++)
+        if (i < 7 || msgbits == 112) S ^= tab.byte_syn[(i + (off >> 3)) * 256 + frame_byte(W, i)];
+    errorbit = 0xFF; nfixed = 0;
+    if (S != 0 && fix_errors && (msgtype == 11 || msgtype == 17 || msgtype == 18)) {
+        const int pmin = off > 5 ? off : 5;             // table positions 5..111 (dump1090.c:806)
+        const int hit = syndrome_pos(tab.fix_hash, S);
+        if (hit >= pmin) {
+            flip_bit(F, hit - off);
+            errorbit = (uint32_t)(hit - off); nfixed = 1; S = 0;
+        } else if (aggressive) {
+            // two flipped bits p < q: S ^ syn[p] must be the syndrome of some q; first p wins
+            for (int p = pmin; p < 112; p++) {
+                const int q = syndrome_pos(tab.fix_hash, S ^ tab.bit_syn[p]);
+                if (q > p) {
+                    flip_bit(F, p - off); flip_bit(F, q - off);
+                    errorbit = (uint32_t)(p - off); nfixed = 2; S = 0;
+                    break;
+                }
+            }
+        }
+    }
+    crc = S;
+}
+
+// One attempt after slicing: message type, delta gate (dump1090.c:1713-1726), CRC and repair.
+MODES_SERIAL_FN void judge_sliced(const uint32_t Fs[4], uint32_t tri, uint32_t sum56, uint32_t sum112, int fix_errors,
+                                  int aggressive, const Tables &tab, Verdict &R) {
+    R.F[0] = Fs[0]; R.F[1] = Fs[1]; R.F[2] = Fs[2]; R.F[3] = Fs[3];
+    R.msgtype = bitrev(Fs[0]) >> 27;
+    const int msgbits = (R.msgtype >= 16 && R.msgtype <= 21) ? 112 : 56;       // dump1090.c:746-753
+    const uint32_t delta = (msgbits == 112) ? sum112 / 56u : sum56 / 28u;       // :1713-1718
+    R.flags = tri ? MODES_EVAL_ERRORS : 0;
+    R.crc = 0; R.errorbit = 0xFF; R.nfixed = 0;
+    if (delta >= 2550u) {                                                       // :1723
+        R.flags |= MODES_EVAL_GATE_OK;
+        if (!tri || aggressive) {                                               // :1731 (errors is 0 or 1)
+            R.flags |= MODES_EVAL_DECODED;
+            crc_and_fix(R.F, msgbits, R.msgtype, fix_errors, aggressive, tab, R.crc, R.errorbit, R.nfixed);
+        }
+    }
+}
+
+MODES_SERIAL_FN bool unconditionally_good(const Verdict &R) {
+    return (R.flags & MODES_EVAL_DECODED) && R.crc == 0 && (R.msgtype == 11 || R.msgtype == 17 || R.msgtype == 18);
+}
+
+// The six 32-bit words of a modes_frame_eval as laid out in memory.
+MODES_SERIAL_FN void eval_words(const Verdict &R, uint32_t w[6]) {
+    const uint32_t W0 = bitrev(R.F[0]), W1 = bitrev(R.F[1]), W2 = bitrev(R.F[2]), W3 = bitrev(R.F[3]) & 0xffff0000u;
+    w[0] = bswap(W0); w[1] = bswap(W1); w[2] = bswap(W2);              // big-endian words -> bytes in memory order
+    w[3] = (W3 >> 24) | ((W3 >> 8) & 0xff00u) | ((R.msgtype & 0xffu) << 16) | ((R.flags & 0xffu) << 24);
+    w[4] = (R.errorbit & 0xffu) | ((R.nfixed & 0xffu) << 8);
+    w[5] = R.crc & 0xffffffu;
+}
+
+MODES_SERIAL_FN uint32_t scale_sample(uint32_t v, uint32_t s) {               // dump1090.c:1473-1476
+    const uint32_t r = (v * s) >> 14;
+    return r > 65535u ? 65535u : r;
+}
+
+// "bits[0] == 2" (dump1090.c:1681): the first pair is a tie.  The 2 is copied into every
+// following indefinite bit (:1675); packed with << (7 - k%8) (:1696-1706) a 2 at bit k sets bit
+// k-1 unless k starts a byte, and leaves bit k clear.  `pairs` holds the magnitude pairs.
+MODES_SERIAL_FN void spread_tie(const uint32_t *pairs, uint32_t F[4]) {
+    for (int k = 1; k < 112; k++) {
+        const uint32_t m = pairs[k];
+        int d = (int)(m & 0xffffu) - (int)(m >> 16);
+        d = d < 0 ? -d : d;
+        if (d >= 256) break;                             // definite: the run ends
+        if (k & 7) { const int b = k - 1; const uint32_t bit = 1u << (b & 31); const int w = b >> 5;
+                     F[0] |= (w == 0) ? bit : 0u; F[1] |= (w == 1) ? bit : 0u; F[2] |= (w == 2) ? bit : 0u; F[3] |= (w == 3) ? bit : 0u; }
+    }
+}
+
+// OR sixteen frame bits (bits 16k .. 16k+15) into F without dynamic register indexing.
+MODES_SERIAL_FN void put16(uint32_t F[4], int k, uint32_t f16) {
+    const uint32_t v = f16 << ((k & 1) * 16);
+    const int w = k >> 1;
+    F[0] |= (w == 0) ? v : 0u; F[1] |= (w == 1) ? v : 0u;
+    F[2] |= (w == 2) ? v : 0u; F[3] |= (w == 3) ? v : 0u;
+}
+
+// The three per-bit loops below handle the 112 bits as 7 blocks of 16 (the block body is
+// unrolled, the block loop is not: ~50 instructions per block keeps the kernel small).
+
+// First pass, block k: raw samples -> magnitude pairs (stored back into the window) -> sliced
+// bits (dump1090.c:1667-1690); accumulates the delta sums (:1692-1693).
+MODES_SERIAL_FN uint32_t first_pass_block(uint32_t *win, int k, uint32_t shift, const uint16_t *lutn, uint32_t &wa,
+                                          uint32_t &prev, uint32_t &dsum, uint32_t &d56) {
+    uint32_t f = 0;
+    uint32_t *p = win + 8 + 16 * k;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t wb = p[i + 1];
+        const uint32_t a = absdiff127x4(funnel(wa, wb, shift));
+        wa = wb;
+        const int lo = (int)ld_ro(lutn + dot4(a & 0x0000ffffu, a));
+        const int hi = (int)ld_ro(lutn + dot4(a & 0xffff0000u, a));
+        p[i] = (uint32_t)lo | ((uint32_t)hi << 16);
+        int d = lo - hi; d = d < 0 ? -d : d;
+        dsum += (uint32_t)d;
+        if (i == 7 && k == 3) d56 = dsum;                                      // bits 0..55 (:1716)
+        bool definite = d >= 256;
+        if (i == 0) definite = definite || k == 0;                             // bit 0 is always taken (:1675)
+        prev = definite ? (uint32_t)(lo > hi) : prev;
+        f |= prev << i;
+    }
+    return f;
+}
+
+// Slice block k from (corrected) magnitude pairs; `prev` carries the last definite decision.
+MODES_SERIAL_FN uint32_t slice_block(const uint32_t *pairs, int k, uint32_t &prev) {
+    uint32_t f = 0;
+    const uint32_t *p = pairs + 16 * k;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t m = p[i];
+        const int lo = (int)(m & 0xffffu), hi = (int)(m >> 16);
+        int d = lo - hi; d = d < 0 ? -d : d;
+        prev = (d >= 256) ? (uint32_t)(lo > hi) : prev;                        // :1675
+        f |= prev << i;
+    }
+    return f;
+}
+
+// Phase correction (dump1090.c:1498-1558), one block of 16 bits walking from *p in direction
+// `step` (+1 forwards along the frame, -1 backwards): the half-bit sample next to the previous
+// decision is rescaled by f_one or f_zero according to that decision.  Rewrites the pairs.
+MODES_SERIAL_FN void correct_block(uint32_t *p, int step, bool fwd, uint32_t f_one, uint32_t f_zero, uint32_t &prev_e) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t m = p[i * step];
+        const uint32_t lo = m & 0xffffu, hi = m >> 16;
+        const uint32_t xs = scale_sample(fwd ? lo : hi, prev_e ? f_one : f_zero);
+        const uint32_t nlo = fwd ? xs : lo, nhi = fwd ? hi : xs;
+        prev_e = (uint32_t)(nlo > nhi);
+        p[i * step] = nlo | (nhi << 16);
+    }
+}
+
+MODES_SERIAL_FN uint32_t window_sample(const uint32_t *win, uint32_t odd, int w) {
+    const uint32_t h = (uint32_t)w + odd;
+    const uint32_t word = win[h >> 1];
+    return (h & 1u) ? (word >> 16) : (word & 0xffffu);
+}
+
+MODES_SERIAL_FN uint32_t magnitude_of(const uint16_t *lutn, uint32_t iq) {
+    const uint32_t a = absdiff127x4(iq | 0x7f7f0000u);
+    return ld_ro(lutn + dot4(a, a));
+}
+
+// Evaluate one candidate.  win: its kWindowWords staged words (modified); odd: see above;
+// at_buffer_start: j == 0, where the reference retries without correcting (dump1090.c:1660);
+// rec: the 12 words of pass[0] and pass[1] of its modes_candidate.
+MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start, int fix_errors, int aggressive,
+                              const Tables &tab, uint32_t rec[12]) {
+    const uint32_t shift = odd ? 32u : 16u;
+    uint32_t F[4] = {0u, 0u, 0u, 0u};
+    uint32_t prev = 0, dsum = 0, d56 = 0;
+    uint32_t wa = win[8];
+#pragma unroll 1
+    for (int k = 0; k < 7; k++) put16(F, k, first_pass_block(win, k, shift, tab.lutn, wa, prev, dsum, d56));
+    const uint32_t d112 = dsum;
+    uint32_t *pairs = win + 8;
+    const uint32_t tri1 = (pairs[0] & 0xffffu) == (pairs[0] >> 16);
+    if (tri1) spread_tie(pairs, F);
+
+    Verdict P1, P2;
+    judge_sliced(F, tri1, d56, d112, fix_errors, aggressive, tab, P1);
+    P2.F[0] = P2.F[1] = P2.F[2] = P2.F[3] = 0;
+    P2.msgtype = 0; P2.flags = 0; P2.errorbit = 0; P2.nfixed = 0; P2.crc = 0;
+
+    if ((P1.flags & MODES_EVAL_GATE_OK) && !unconditionally_good(P1)) {
+        P1.flags |= MODES_EVAL_P2_VALID;
+        if (at_buffer_start) {
+            P2 = P1;
+            P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
+        } else {
+            // applyPhaseCorrection, dump1090.c:1498-1558
+            const uint32_t m_1 = magnitude_of(tab.lutn, window_sample(win, odd, 0));
+            const uint32_t m0 = magnitude_of(tab.lutn, window_sample(win, odd, 1));
+            const uint32_t m2 = magnitude_of(tab.lutn, window_sample(win, odd, 3));
+            const uint32_t m3 = magnitude_of(tab.lutn, window_sample(win, odd, 4));
+            const uint32_t m6 = magnitude_of(tab.lutn, window_sample(win, odd, 7));
+            const uint32_t m7 = magnitude_of(tab.lutn, window_sample(win, odd, 8));
+            const uint32_t m9 = magnitude_of(tab.lutn, window_sample(win, odd, 10));
+            const uint32_t m10 = magnitude_of(tab.lutn, window_sample(win, odd, 11));
+            const uint32_t on_time = m0 + m2 + m7 + m9;
+            const uint32_t early = (m_1 + m6) * 2u, late = (m3 + m10) * 2u;
+            // early > late: walk backwards, the second half-bit samples are rescaled;
+            // otherwise forwards, the first half-bit samples are.
+            const bool fwd = !(early > late);
+            const uint32_t lead = fwd ? late : early;
+            const uint32_t q = 16384u * lead / (lead + on_time);
+            const uint32_t up = (16384u + q) & 0xffffu, down = (16384u - q) & 0xffffu;
+            // forwards a previous 1 scales up, backwards a following 1 scales down; the first
+            // bit handled always scales up
+            const uint32_t f_one = fwd ? up : down, f_zero = fwd ? down : up;
+            uint32_t prev_e = fwd ? 1u : 0u;
+            const int step = fwd ? 1 : -1;
+            uint32_t *cp = fwd ? pairs : pairs + 111;
+#pragma unroll 1
+            for (int k = 0; k < 7; k++, cp += 16 * step) correct_block(cp, step, fwd, f_one, f_zero, prev_e);
+            uint32_t G[4] = {0u, 0u, 0u, 0u};
+            const uint32_t tri2 = (pairs[0] & 0xffffu) == (pairs[0] >> 16);
+            uint32_t pv = (uint32_t)((pairs[0] & 0xffffu) > (pairs[0] >> 16));  // bit 0 is always taken
+#pragma unroll 1
+            for (int k = 0; k < 7; k++) put16(G, k, slice_block(pairs, k, pv));
+            if (tri2) spread_tie(pairs, G);
+            if (G[0] == F[0] && G[1] == F[1] && G[2] == F[2] && G[3] == F[3] && tri2 == tri1) {
+                P2 = P1;                                 // same bits, same (uncorrected) delta sums: same verdict
+                P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
+            } else {
+                judge_sliced(G, tri2, d56, d112, fix_errors, aggressive, tab, P2);
+            }
+        }
+    }
+    eval_words(P1, rec);
+    eval_words(P2, rec + 6);
+}
+
+}  // namespace serial
+}  // namespace modes

@@ -13,6 +13,7 @@
 //   * the sink gate (dump1090.c:1803) and struct modesMessage field decode
 //     (:1133-1179, :1212-1308) for delivered messages
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -214,8 +215,11 @@ class BuildPool {
     }
   private:
     BuildPool() {
+        // message structs are ~200 B of stores each: a handful of threads saturates one socket's
+        // write bandwidth.  MODES_BUILD_THREADS overrides (total threads, including the caller).
         unsigned hw = std::thread::hardware_concurrency();
-        unsigned nw = hw > 16 ? 7 : (hw > 2 ? hw / 2 - 1 : 0);
+        unsigned nw = hw > 32 ? 15 : (hw > 16 ? 7 : (hw > 2 ? hw / 2 - 1 : 0));
+        if (const char *e = std::getenv("MODES_BUILD_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) nw = (unsigned)v - 1; }
         for (unsigned i = 0; i < nw; i++) workers_.emplace_back([this] { loop(); });
         for (auto &t : workers_) t.detach();
     }
@@ -315,8 +319,15 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
                         const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out) {
     static thread_local std::vector<Delivery> deliveries;
     deliveries.clear();
+    static const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, deliveries);
+    const auto t1 = std::chrono::steady_clock::now();
     deliver(deliveries, out);
+    if (timing)
+        std::fprintf(stderr, "resolve_candidates: %zu tiles, verdicts %.2f ms, structs %.2f ms\n", n_tiles,
+                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 }
 
 // Several shards of one stream (e.g. one per GPU), resolved concurrently and exactly.
@@ -331,8 +342,12 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
 void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
                     const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
                     MessageOut &out) {
-    struct Run { ResolveState start, end; std::vector<Delivery> deliveries; bool verified = false; };
-    std::vector<Run> runs(n_shards);
+    // Delivery lists keep their capacity from call to call (growing them from nothing in every
+    // call costs more in page faults, taken concurrently by the shard threads, than the verdicts).
+    struct Run { ResolveState start, end; std::vector<Delivery> deliveries; };
+    static thread_local std::vector<Run> run_store;
+    if (run_store.size() < n_shards) run_store.resize(n_shards);
+    Run *const runs = run_store.data();                    // the shard threads must see THIS thread's store
     ResolveState blank;
     blank.reset();
     auto run_shard = [&](size_t k, const ResolveState &from) {
@@ -341,10 +356,16 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
         std::memset(r.start.stats, 0, sizeof(r.start.stats));
         r.end = r.start;
         r.deliveries.clear();
+        const auto t0 = std::chrono::steady_clock::now();
         judge_tiles(r.end, cfg, cands[k], tiles[k], n_tiles[k], buffer_base[k], r.deliveries);
+        if (std::getenv("MODES_RESOLVE_TIMING2")) std::fprintf(stderr, "  shard %zu: %.2f ms\n", k, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };
+    static const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto t_start = now();
+    int rounds = 0;
     size_t done = 0;                                       // shards [0, done) are final
-    for (int round = 0; done < n_shards; round++) {
+    for (int round = 0; done < n_shards; round++, rounds++) {
         // fix every guess before any thread of this round starts rewriting runs[*].end
         std::vector<ResolveState> guess(n_shards);
         std::vector<char> rerun(n_shards, 0);
@@ -362,10 +383,15 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
             if (std::memcmp(truth.icao, runs[done].start.icao, sizeof(truth.icao)) != 0) break;
         }
     }
+    auto t_judged = now();
     for (size_t k = 0; k < n_shards; k++) {
         for (int i = 0; i < 8; i++) st.stats[i] += runs[k].end.stats[i];
         deliver(runs[k].deliveries, out);
     }
+    if (timing)
+        std::fprintf(stderr, "resolve_shards: %zu shards, %d rounds, verdicts %.2f ms, structs %.2f ms\n", n_shards, rounds,
+                     std::chrono::duration<double, std::milli>(t_judged - t_start).count(),
+                     std::chrono::duration<double, std::milli>(now() - t_judged).count());
     if (n_shards) {
         std::memcpy(st.icao, runs[n_shards - 1].end.icao, sizeof(st.icao));
         st.cur_buffer = runs[n_shards - 1].end.cur_buffer;
