@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include "modes_internal.h"
+#include "modes_eval_serial.cuh"
 
 namespace modes {
 
@@ -822,11 +823,123 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
     }
 }
 
+// ---- K2, one thread per candidate ----------------------------------------------------------
+// The evaluation itself is modes_eval_serial.cuh (sequential code over one candidate's window).
+// A warp takes 32 consecutive candidates: their windows are staged in shared memory with
+// coalesced loads (row stride 123 words, so that lane l walking its own row hits bank 27l+k:
+// conflict free), every lane evaluates its own candidate, and the 32 records leave through the
+// same shared memory as one contiguous 1792-byte store.  Chunks of 32 are handed out from a global
+// counter, the next one requested before the current one is staged.
+constexpr int kSerWarps = 6;
+constexpr int kSerThreads = 32 * kSerWarps;
+constexpr int kSerRow = 123;
+constexpr int kSerTableWords = 112 + kFixHashSlots + 14 * 256;
+constexpr int kSerSmemBytes = 4 * (kSerTableWords + kSerWarps * 32 * kSerRow);
+
+__device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
+    const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);
+    return *reinterpret_cast<const uint16_t *>(p);
+}
+
+__global__ void __launch_bounds__(kSerThreads, 2)
+eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
+                   uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_bsyn = s_hash + kFixHashSlots, *s_win = s_bsyn + 14 * 256;
+    for (int i = threadIdx.x; i < 112; i += kSerThreads) s_syn[i] = tab.bit_syn[i];
+    for (int i = threadIdx.x; i < kFixHashSlots; i += kSerThreads) s_hash[i] = tab.fix_hash[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 14 * 256; i += kSerThreads) s_bsyn[i] = serial::byte_syndrome(s_syn, i >> 8, i & 255);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *wwin = s_win + warp * 32 * kSerRow;
+    const serial::Tables T{tab.lutn, s_syn, s_bsyn, s_hash};
+    uint32_t n_cand = counters[0];
+    if (n_cand > cand_capacity) n_cand = cand_capacity;
+    const uint32_t n_chunks = (n_cand + 31) / 32;
+    const uint32_t total_warps = gridDim.x * kSerWarps;
+    const uint32_t *body32 = reinterpret_cast<const uint32_t *>(in.body);
+
+    uint32_t chunk = blockIdx.x * kSerWarps + warp;
+    while (chunk < n_chunks) {
+        uint32_t next = 0;
+        if (lane == 0) next = total_warps + atomicAdd(&counters[3], 1u);
+        const uint32_t base = chunk * 32;
+        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;
+        const uint32_t my_v = cand_v[base + ((uint32_t)lane < n ? lane : n - 1)];   // idle lanes of the last chunk duplicate its last candidate
+
+        // stage the windows: row c = candidate c, words (first>>1) .. +120 of the body
+        if (__all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples)) {
+            // common case (no window in the carry block): branch-free, four rows in flight
+#pragma unroll 4
+            for (int c = 0; c < 32; c++) {
+                const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
+                const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
+                uint32_t *row = wwin + c * kSerRow;
+                const uint32_t w0 = __ldg(wp + lane), w1 = __ldg(wp + 32 + lane), w2 = __ldg(wp + 64 + lane);
+                const uint32_t w3 = lane < serial::kWindowWords - 96 ? __ldg(wp + 96 + lane) : 0u;
+                row[lane] = w0; row[32 + lane] = w1; row[64 + lane] = w2;
+                if (lane < serial::kWindowWords - 96) row[96 + lane] = w3;
+            }
+        } else {
+            for (uint32_t c = 0; c < n; c++) {
+                const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
+                uint32_t *row = wwin + c * kSerRow;
+                if (v > (uint32_t)kHaloSamples) {
+                    const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
+                    for (int k = lane; k < serial::kWindowWords; k += 32) row[k] = __ldg(wp + k);
+                } else {
+                    // window reaches into the carry block (first 240 positions of a batch): sample by sample, odd = 0
+                    for (int k = lane; k < serial::kWindowWords; k += 32)
+                        row[k] = raw_sample(in, (uint64_t)v - 1 + 2 * k) | (raw_sample(in, (uint64_t)v + 2 * k) << 16);
+                }
+            }
+        }
+        __syncwarp();
+
+        uint32_t rec[14];
+        if ((uint32_t)lane < n) {
+            const uint64_t t = (uint64_t)my_v - 2;
+            const uint32_t odd = my_v > (uint32_t)kHaloSamples ? ((my_v - 1 - kHaloSamples) & 1u) : 0u;
+            rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
+            serial::evaluate(wwin + lane * kSerRow, odd, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive,
+                             T, rec + 2);
+        }
+        __syncwarp();
+        if ((uint32_t)lane < n) {
+#pragma unroll
+            for (int k = 0; k < 14; k += 2) *reinterpret_cast<uint2 *>(wwin + 14 * lane + k) = make_uint2(rec[k], rec[k + 1]);
+        }
+        __syncwarp();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(records + base);
+        for (uint32_t i = lane; i < n * 14; i += 32) dst[i] = wwin[i];
+        __syncwarp();
+        chunk = __shfl_sync(0xffffffffu, next, 0);
+    }
+}
+
+// MODES_EVAL_VARIANT=warp selects the warp-per-candidate kernel (the first formulation; kept for
+// comparison and as a second implementation in the parity tests).
+static int eval_variant() {                       // read per launch (tests switch it within one process)
+    const char *e = std::getenv("MODES_EVAL_VARIANT");
+    return (e && e[0] == 'w') ? 1 : 0;
+}
+
 void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
                  modes_candidate *records, int fix_errors, int aggressive, int sm_count,
                  cudaStream_t stream) {
-    eval_kernel<<<sm_count * 4, kEvalThreads, 0, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
-                                                          records, fix_errors, aggressive);
+    if (eval_variant() == 1) {
+        eval_kernel<<<sm_count * 4, kEvalThreads, 0, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
+                                                              records, fix_errors, aggressive);
+        return;
+    }
+    static const bool configured = [] {
+        return cudaFuncSetAttribute(eval_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes) == cudaSuccess;
+    }();
+    (void)configured;
+    eval_serial_kernel<<<sm_count * 2, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
+                                                                            scan.cand_capacity, records, fix_errors, aggressive);
 }
 
 // ------------------------------------------------------- magnitude (tests)

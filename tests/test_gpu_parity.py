@@ -44,9 +44,12 @@ def test_decode_matches_oracle(name, kw, gpu_decoder_factory, checker_libs):
 
 @pytest.mark.parametrize("name", list(STREAMS))
 @pytest.mark.parametrize("aggressive", [0, 1])
-def test_candidates_match_oracle(name, aggressive, gpu_decoder_factory, checker_libs):
-    """Scan + frame-evaluation kernels: candidate set and both evaluated passes, record for record."""
+@pytest.mark.parametrize("variant", ["serial", "warp"])
+def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory, checker_libs, monkeypatch):
+    """Scan + frame-evaluation kernels: candidate set and both evaluated passes, record for record.
+    Both frame-evaluation kernels (thread per candidate, the default; warp per candidate)."""
     import torch
+    monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
     data = STREAMS[name]
     nbuf = data.size // api.BUFFER_BYTES + 1
     padded = np.full(nbuf * api.BUFFER_BYTES, 127, dtype=np.uint8)
