@@ -30,10 +30,8 @@ MODES_SERIAL_FN uint32_t bitrev(uint32_t x) { return __brev(x); }
 // (hi:lo) >> s for s in {16, 32}
 MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
 MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return __byte_perm(x, 0u, 0x0123u); }
-MODES_SERIAL_FN uint32_t ld_ro(const uint16_t *p) { return __ldg(p); }
 #else
 MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24); }
-MODES_SERIAL_FN uint32_t ld_ro(const uint16_t *p) { return *p; }
 MODES_SERIAL_FN uint32_t absdiff127x4(uint32_t w) {
     uint32_t r = 0;
     for (int k = 0; k < 4; k++) {
@@ -66,12 +64,18 @@ MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) {
 // (first | second << 16) instead; words 0..7 keep the raw preamble samples.
 constexpr int kWindowWords = 121;
 
+constexpr int kIqLutEntries = 129 * 129;
+
 struct Tables {
-    const uint16_t *lutn;        // [32769] magnitude by i*i+q*q (dump1090.c:362)
+    const uint16_t *lut_iq;      // [129*129] magnitude by (|I-127|, |Q-127|): round(sqrt(i*i+q*q)*360), dump1090.c:362
     const uint32_t *bit_syn;     // [112]   syndrome of one flipped bit
-    const uint32_t *byte_syn;    // [14*256] syndrome of byte value x at frame byte i: XOR of bit_syn over its set bits
+    const uint32_t *nib_syn;     // [28*16] syndrome of nibble value x at frame nibble i: XOR of bit_syn over its set bits
     const uint32_t *fix_hash;    // [256]   inverse of bit_syn over positions 5..111
 };
+
+// Index into lut_iq of the sample held in the low (kLutLow) or high (kLutHigh) half of a word of
+// |byte - 127| values: 129 * |I-127| + |Q-127| as one byte dot product.
+constexpr uint32_t kLutLow = 0x00000181u, kLutHigh = 0x01810000u;
 
 // What one attempt (uncorrected, or phase corrected) yields: the six 32-bit words of a
 // modes_frame_eval (include/modes_b200.h) are made from it by eval_words().
@@ -80,11 +84,11 @@ struct Verdict {
     uint32_t msgtype, flags, errorbit, nfixed, crc;
 };
 
-// Entry (pos, value) of Tables::byte_syn from the bit syndromes: bit 7-k of the byte is frame bit 8*pos+k.
-MODES_SERIAL_FN uint32_t byte_syndrome(const uint32_t *bit_syn, int pos, uint32_t value) {
+// Entry (pos, value) of Tables::nib_syn from the bit syndromes: bit 3-k of the nibble is frame bit 4*pos+k.
+MODES_SERIAL_FN uint32_t nibble_syndrome(const uint32_t *bit_syn, int pos, uint32_t value) {
     uint32_t x = 0;
 #pragma unroll
-    for (int k = 0; k < 8; k++) x ^= ((value >> (7 - k)) & 1u) ? bit_syn[8 * pos + k] : 0u;
+    for (int k = 0; k < 4; k++) x ^= ((value >> (3 - k)) & 1u) ? bit_syn[4 * pos + k] : 0u;
     return x;
 }
 
@@ -109,10 +113,10 @@ MODES_SERIAL_FN void flip_bit(uint32_t F[4], int b) {
     F[2] ^= (w == 2) ? m : 0u; F[3] ^= (w == 3) ? m : 0u;
 }
 
-// Frame byte i (0..13) of F: bit 8i is its most significant bit.
-MODES_SERIAL_FN uint32_t frame_byte(const uint32_t W[4], int i) {        // W = bit-reversed F words
-    const uint32_t w = (i < 4) ? W[0] : (i < 8) ? W[1] : (i < 12) ? W[2] : W[3];
-    return (w >> (24 - 8 * (i & 3))) & 0xffu;
+// Frame nibble i (0..27) of F: bit 4i is its most significant bit.
+MODES_SERIAL_FN uint32_t frame_nibble(const uint32_t W[4], int i) {      // W = bit-reversed F words
+    const uint32_t w = (i < 8) ? W[0] : (i < 16) ? W[1] : (i < 24) ? W[2] : W[3];
+    return (w >> (28 - 4 * (i & 7))) & 0xfu;
 }
 
 // CRC syndrome of the first msgbits of F, then the repairs of dump1090.c:1114-1126 (:733-742
@@ -123,8 +127,8 @@ MODES_SERIAL_FN void crc_and_fix(uint32_t F[4], int msgbits, uint32_t msgtype, i
     const uint32_t W[4] = {bitrev(F[0]), bitrev(F[1]), bitrev(F[2]), bitrev(F[3])};
     uint32_t S = 0;
 #pragma unroll
-    for (int i = 0; i < 14; i++)
-        if (i < 7 || msgbits == 112) S ^= tab.byte_syn[(i + (off >> 3)) * 256 + frame_byte(W, i)];
+    for (int i = 0; i < 28; i++)
+        if (i < 14 || msgbits == 112) S ^= tab.nib_syn[(i + (off >> 2)) * 16 + frame_nibble(W, i)];
     errorbit = 0xFF; nfixed = 0;
     if (S != 0 && fix_errors && (msgtype == 11 || msgtype == 17 || msgtype == 18)) {
         const int pmin = off > 5 ? off : 5;             // table positions 5..111 (dump1090.c:806)
@@ -210,7 +214,7 @@ MODES_SERIAL_FN void put16(uint32_t F[4], int k, uint32_t f16) {
 
 // First pass, block k: raw samples -> magnitude pairs (stored back into the window) -> sliced
 // bits (dump1090.c:1667-1690); accumulates the delta sums (:1692-1693).
-MODES_SERIAL_FN uint32_t first_pass_block(uint32_t *win, int k, uint32_t shift, const uint16_t *lutn, uint32_t &wa,
+MODES_SERIAL_FN uint32_t first_pass_block(uint32_t *win, int k, uint32_t shift, const uint16_t *lut_iq, uint32_t &wa,
                                           uint32_t &prev, uint32_t &dsum, uint32_t &d56) {
     uint32_t f = 0;
     uint32_t *p = win + 8 + 16 * k;
@@ -219,8 +223,8 @@ MODES_SERIAL_FN uint32_t first_pass_block(uint32_t *win, int k, uint32_t shift, 
         const uint32_t wb = p[i + 1];
         const uint32_t a = absdiff127x4(funnel(wa, wb, shift));
         wa = wb;
-        const int lo = (int)ld_ro(lutn + dot4(a & 0x0000ffffu, a));
-        const int hi = (int)ld_ro(lutn + dot4(a & 0xffff0000u, a));
+        const int lo = (int)lut_iq[dot4(a, kLutLow)];
+        const int hi = (int)lut_iq[dot4(a, kLutHigh)];
         p[i] = (uint32_t)lo | ((uint32_t)hi << 16);
         int d = lo - hi; d = d < 0 ? -d : d;
         dsum += (uint32_t)d;
@@ -233,34 +237,53 @@ MODES_SERIAL_FN uint32_t first_pass_block(uint32_t *win, int k, uint32_t shift, 
     return f;
 }
 
-// Slice block k from (corrected) magnitude pairs; `prev` carries the last definite decision.
-MODES_SERIAL_FN uint32_t slice_block(const uint32_t *pairs, int k, uint32_t &prev) {
-    uint32_t f = 0;
-    const uint32_t *p = pairs + 16 * k;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const uint32_t m = p[i];
-        const int lo = (int)(m & 0xffffu), hi = (int)(m >> 16);
-        int d = lo - hi; d = d < 0 ? -d : d;
-        prev = (d >= 256) ? (uint32_t)(lo > hi) : prev;                        // :1675
-        f |= prev << i;
-    }
-    return f;
-}
-
-// Phase correction (dump1090.c:1498-1558), one block of 16 bits walking from *p in direction
-// `step` (+1 forwards along the frame, -1 backwards): the half-bit sample next to the previous
-// decision is rescaled by f_one or f_zero according to that decision.  Rewrites the pairs.
-MODES_SERIAL_FN void correct_block(uint32_t *p, int step, bool fwd, uint32_t f_one, uint32_t f_zero, uint32_t &prev_e) {
+// Phase correction (dump1090.c:1498-1558) and slicing of the corrected samples, one block of 16
+// bits walking from *p in direction `step` (+1 forwards along the frame, -1 backwards): the
+// half-bit sample next to the previous decision is rescaled by f_one or f_zero according to that
+// decision, then the corrected pair is classified like the first pass (:1675): `d16` collects the
+// definite bits, `o16` the definite ones, both in walk order.  `end0` / `end15` say that the
+// first / last bit of the block is bit 0 of the frame (always definite; a tie there is the
+// tri-state of :1681).
+MODES_SERIAL_FN void correct_slice_block(const uint32_t *p, int step, bool fwd, bool end0, bool end15, uint32_t f_one,
+                                         uint32_t f_zero, uint32_t &prev_e, uint32_t &d16, uint32_t &o16, uint32_t &tie0) {
+    d16 = 0; o16 = 0;
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const uint32_t m = p[i * step];
         const uint32_t lo = m & 0xffffu, hi = m >> 16;
         const uint32_t xs = scale_sample(fwd ? lo : hi, prev_e ? f_one : f_zero);
-        const uint32_t nlo = fwd ? xs : lo, nhi = fwd ? hi : xs;
+        const int nlo = (int)(fwd ? xs : lo), nhi = (int)(fwd ? hi : xs);
         prev_e = (uint32_t)(nlo > nhi);
-        p[i * step] = nlo | (nhi << 16);
+        int d = nlo - nhi; d = d < 0 ? -d : d;
+        bool definite = d >= 256;
+        if (i == 0 && end0) { definite = true; tie0 = (uint32_t)(nlo == nhi); }
+        if (i == 15 && end15) { definite = true; tie0 = (uint32_t)(nlo == nhi); }
+        d16 |= (uint32_t)definite << i;
+        o16 |= (uint32_t)(definite && nlo > nhi) << i;
     }
+}
+
+// Bits with D=1 are definite and take their value from O; bits with D=0 copy the nearest
+// definite bit below (:1675).  That is the carry into each bit of (O|~D) + O.  Bit 0 must be in D.
+MODES_SERIAL_FN void fill_copies(const uint32_t D[4], const uint32_t O[4], uint32_t F[4]) {
+    const uint64_t d0 = D[0] | ((uint64_t)D[1] << 32), d1 = D[2] | ((uint64_t)D[3] << 32);
+    const uint64_t o0 = O[0] | ((uint64_t)O[1] << 32), o1 = O[2] | ((uint64_t)O[3] << 32);
+    const uint64_t a0 = o0 | ~d0, a1 = o1 | ~d1;
+    const uint64_t s0 = a0 + o0;
+    const uint64_t s1 = a1 + o1 + (s0 < a0 ? 1ull : 0ull);
+    const uint64_t ci0 = s0 ^ a0 ^ o0, ci1 = s1 ^ a1 ^ o1;                   // carry INTO each bit
+    const uint64_t f0 = (ci0 >> 1) | (ci1 << 63), f1 = (ci1 >> 1) & 0x0000ffffffffffffull;
+    F[0] = (uint32_t)f0; F[1] = (uint32_t)(f0 >> 32); F[2] = (uint32_t)f1; F[3] = (uint32_t)(f1 >> 32);
+}
+
+// spread_tie on the definite mask instead of the pairs: the run of indefinite bits after bit 0.
+MODES_SERIAL_FN void spread_tie_mask(const uint32_t D[4], uint32_t F[4]) {
+    const uint64_t t0 = ~(D[0] | ((uint64_t)D[1] << 32)) | 1ull, t1 = ~(D[2] | ((uint64_t)D[3] << 32));
+    const uint64_t u0 = t0 + 1ull, u1 = t1 + (u0 == 0 ? 1ull : 0ull);
+    const uint64_t run0 = t0 & ~u0, run1 = (u0 == 0) ? (t1 & ~u1) : 0ull;       // bits 0..r
+    const uint64_t e0 = ((run0 >> 1) | (run1 << 63)) & 0x7f7f7f7f7f7f7f7full;
+    const uint64_t e1 = (run1 >> 1) & 0x00007f7f7f7f7f7full;
+    F[0] |= (uint32_t)e0; F[1] |= (uint32_t)(e0 >> 32); F[2] |= (uint32_t)e1; F[3] |= (uint32_t)(e1 >> 32);
 }
 
 MODES_SERIAL_FN uint32_t window_sample(const uint32_t *win, uint32_t odd, int w) {
@@ -269,9 +292,8 @@ MODES_SERIAL_FN uint32_t window_sample(const uint32_t *win, uint32_t odd, int w)
     return (h & 1u) ? (word >> 16) : (word & 0xffffu);
 }
 
-MODES_SERIAL_FN uint32_t magnitude_of(const uint16_t *lutn, uint32_t iq) {
-    const uint32_t a = absdiff127x4(iq | 0x7f7f0000u);
-    return ld_ro(lutn + dot4(a, a));
+MODES_SERIAL_FN uint32_t magnitude_of(const uint16_t *lut_iq, uint32_t iq) {
+    return lut_iq[dot4(absdiff127x4(iq | 0x7f7f0000u), kLutLow)];
 }
 
 // Evaluate one candidate.  win: its kWindowWords staged words (modified); odd: see above;
@@ -284,7 +306,7 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
     uint32_t prev = 0, dsum = 0, d56 = 0;
     uint32_t wa = win[8];
 #pragma unroll 1
-    for (int k = 0; k < 7; k++) put16(F, k, first_pass_block(win, k, shift, tab.lutn, wa, prev, dsum, d56));
+    for (int k = 0; k < 7; k++) put16(F, k, first_pass_block(win, k, shift, tab.lut_iq, wa, prev, dsum, d56));
     const uint32_t d112 = dsum;
     uint32_t *pairs = win + 8;
     const uint32_t tri1 = (pairs[0] & 0xffffu) == (pairs[0] >> 16);
@@ -302,14 +324,14 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
             P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
         } else {
             // applyPhaseCorrection, dump1090.c:1498-1558
-            const uint32_t m_1 = magnitude_of(tab.lutn, window_sample(win, odd, 0));
-            const uint32_t m0 = magnitude_of(tab.lutn, window_sample(win, odd, 1));
-            const uint32_t m2 = magnitude_of(tab.lutn, window_sample(win, odd, 3));
-            const uint32_t m3 = magnitude_of(tab.lutn, window_sample(win, odd, 4));
-            const uint32_t m6 = magnitude_of(tab.lutn, window_sample(win, odd, 7));
-            const uint32_t m7 = magnitude_of(tab.lutn, window_sample(win, odd, 8));
-            const uint32_t m9 = magnitude_of(tab.lutn, window_sample(win, odd, 10));
-            const uint32_t m10 = magnitude_of(tab.lutn, window_sample(win, odd, 11));
+            const uint32_t m_1 = magnitude_of(tab.lut_iq, window_sample(win, odd, 0));
+            const uint32_t m0 = magnitude_of(tab.lut_iq, window_sample(win, odd, 1));
+            const uint32_t m2 = magnitude_of(tab.lut_iq, window_sample(win, odd, 3));
+            const uint32_t m3 = magnitude_of(tab.lut_iq, window_sample(win, odd, 4));
+            const uint32_t m6 = magnitude_of(tab.lut_iq, window_sample(win, odd, 7));
+            const uint32_t m7 = magnitude_of(tab.lut_iq, window_sample(win, odd, 8));
+            const uint32_t m9 = magnitude_of(tab.lut_iq, window_sample(win, odd, 10));
+            const uint32_t m10 = magnitude_of(tab.lut_iq, window_sample(win, odd, 11));
             const uint32_t on_time = m0 + m2 + m7 + m9;
             const uint32_t early = (m_1 + m6) * 2u, late = (m3 + m10) * 2u;
             // early > late: walk backwards, the second half-bit samples are rescaled;
@@ -323,15 +345,19 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
             const uint32_t f_one = fwd ? up : down, f_zero = fwd ? down : up;
             uint32_t prev_e = fwd ? 1u : 0u;
             const int step = fwd ? 1 : -1;
-            uint32_t *cp = fwd ? pairs : pairs + 111;
+            const uint32_t *cp = fwd ? pairs : pairs + 111;
+            uint32_t Dm[4] = {0u, 0u, 0u, 0u}, Om[4] = {0u, 0u, 0u, 0u}, tri2 = 0;
 #pragma unroll 1
-            for (int k = 0; k < 7; k++, cp += 16 * step) correct_block(cp, step, fwd, f_one, f_zero, prev_e);
-            uint32_t G[4] = {0u, 0u, 0u, 0u};
-            const uint32_t tri2 = (pairs[0] & 0xffffu) == (pairs[0] >> 16);
-            uint32_t pv = (uint32_t)((pairs[0] & 0xffffu) > (pairs[0] >> 16));  // bit 0 is always taken
-#pragma unroll 1
-            for (int k = 0; k < 7; k++) put16(G, k, slice_block(pairs, k, pv));
-            if (tri2) spread_tie(pairs, G);
+            for (int k = 0; k < 7; k++, cp += 16 * step) {
+                uint32_t d16, o16;
+                correct_slice_block(cp, step, fwd, fwd && k == 0, !fwd && k == 6, f_one, f_zero, prev_e, d16, o16, tri2);
+                if (!fwd) { d16 = bitrev(d16) >> 16; o16 = bitrev(o16) >> 16; }      // walk order -> frame order
+                put16(Dm, fwd ? k : 6 - k, d16);
+                put16(Om, fwd ? k : 6 - k, o16);
+            }
+            uint32_t G[4];
+            fill_copies(Dm, Om, G);
+            if (tri2) spread_tie_mask(Dm, G);
             if (G[0] == F[0] && G[1] == F[1] && G[2] == F[2] && G[3] == F[3] && tri2 == tri1) {
                 P2 = P1;                                 // same bits, same (uncorrected) delta sums: same verdict
                 P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;

@@ -826,14 +826,17 @@ eval_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v,
 // ---- K2, one thread per candidate ----------------------------------------------------------
 // The evaluation itself is modes_eval_serial.cuh (sequential code over one candidate's window).
 // A warp takes 32 consecutive candidates: their windows are staged in shared memory with
-// coalesced loads (row stride 123 words, so that lane l walking its own row hits bank 27l+k:
+// coalesced loads (row stride 121 words, so that lane l walking its own row hits bank 25l+k:
 // conflict free), every lane evaluates its own candidate, and the 32 records leave through the
 // same shared memory as one contiguous 1792-byte store.  Chunks of 32 are handed out from a global
 // counter, the next one requested before the current one is staged.
-constexpr int kSerWarps = 6;
+constexpr int kSerWarps = 12;                          // one CTA per SM
 constexpr int kSerThreads = 32 * kSerWarps;
-constexpr int kSerRow = 123;
-constexpr int kSerTableWords = 112 + kFixHashSlots + 14 * 256;
+constexpr int kSerRow = serial::kWindowWords;          // 121 words: odd, so lane l walking its own row hits bank 25l+k
+constexpr int kSerNibWords = 28 * 16;
+constexpr int kSerLutWords = (serial::kIqLutEntries + 3) / 4 * 2;   // even: the window area stays 8-byte aligned
+static_assert((112 + kFixHashSlots + kSerNibWords + kSerLutWords) % 2 == 0 && (32 * kSerRow) % 2 == 0, "record staging uses 8-byte stores");
+constexpr int kSerTableWords = 112 + kFixHashSlots + kSerNibWords + kSerLutWords;
 constexpr int kSerSmemBytes = 4 * (kSerTableWords + kSerWarps * 32 * kSerRow);
 
 __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
@@ -841,20 +844,28 @@ __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) 
     return *reinterpret_cast<const uint16_t *>(p);
 }
 
-__global__ void __launch_bounds__(kSerThreads, 2)
+__global__ void __launch_bounds__(kSerThreads, 1)
 eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
                    uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
     extern __shared__ __align__(16) uint32_t s_mem[];
-    uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_bsyn = s_hash + kFixHashSlots, *s_win = s_bsyn + 14 * 256;
+    uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_nib = s_hash + kFixHashSlots;
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_nib + kSerNibWords);
+    uint32_t *s_win = s_nib + kSerNibWords + kSerLutWords;
     for (int i = threadIdx.x; i < 112; i += kSerThreads) s_syn[i] = tab.bit_syn[i];
     for (int i = threadIdx.x; i < kFixHashSlots; i += kSerThreads) s_hash[i] = tab.fix_hash[i];
+    // magnitude by (|I-127|, |Q-127|): the 33 KB that the per-thread lookups hit stay in shared memory
+    // (as gathers from the 64 KB table in L1 they were the kernel's bottleneck: ~5 wavefronts each)
+    for (int i = threadIdx.x; i < serial::kIqLutEntries; i += kSerThreads) {
+        const int ai = i / 129, aq = i - 129 * ai;
+        s_lut[i] = __ldg(tab.lutn + ai * ai + aq * aq);
+    }
     __syncthreads();
-    for (int i = threadIdx.x; i < 14 * 256; i += kSerThreads) s_bsyn[i] = serial::byte_syndrome(s_syn, i >> 8, i & 255);
+    for (int i = threadIdx.x; i < kSerNibWords; i += kSerThreads) s_nib[i] = serial::nibble_syndrome(s_syn, i >> 4, i & 15);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wwin = s_win + warp * 32 * kSerRow;
-    const serial::Tables T{tab.lutn, s_syn, s_bsyn, s_hash};
+    const serial::Tables T{s_lut, s_syn, s_nib, s_hash};
     uint32_t n_cand = counters[0];
     if (n_cand > cand_capacity) n_cand = cand_capacity;
     const uint32_t n_chunks = (n_cand + 31) / 32;
@@ -938,7 +949,7 @@ void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs
         return cudaFuncSetAttribute(eval_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes) == cudaSuccess;
     }();
     (void)configured;
-    eval_serial_kernel<<<sm_count * 2, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
+    eval_serial_kernel<<<sm_count, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
                                                                             scan.cand_capacity, records, fix_errors, aggressive);
 }
 

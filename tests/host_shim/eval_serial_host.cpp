@@ -19,17 +19,20 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
     using namespace modes::serial;
     static std::vector<uint16_t> lutn(32769);
     static uint32_t bit_syn[112], fix_hash[256];
-    static std::vector<uint32_t> byte_syn(14 * 256);
+    static std::vector<uint32_t> nib_syn(28 * 16);
+    static std::vector<uint16_t> lut_iq(kIqLutEntries);
     static bool ready = false;
     if (!ready) {
         modes::build_lutn(lutn.data());
         modes::build_bit_syndromes(bit_syn);
         if (!modes::build_fix_hash(bit_syn, fix_hash)) return -1;
-        for (int pos = 0; pos < 14; pos++)
-            for (uint32_t v = 0; v < 256; v++) byte_syn[pos * 256 + v] = byte_syndrome(bit_syn, pos, v);
+        for (int pos = 0; pos < 28; pos++)
+            for (uint32_t v = 0; v < 16; v++) nib_syn[pos * 16 + v] = nibble_syndrome(bit_syn, pos, v);
+        for (int i = 0; i <= 128; i++)
+            for (int q = 0; q <= 128; q++) lut_iq[i * 129 + q] = lutn[i * i + q * q];
         ready = true;
     }
-    const Tables tab{lutn.data(), bit_syn, byte_syn.data(), fix_hash};
+    const Tables tab{lut_iq.data(), bit_syn, nib_syn.data(), fix_hash};
     auto s16 = [&](uint64_t idx) -> uint32_t { uint16_t w; std::memcpy(&w, virt + 2 * idx, 2); return w; };
     for (uint32_t c = 0; c < n; c++) {
         const uint32_t v = cand_v[c];
