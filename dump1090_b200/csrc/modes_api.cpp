@@ -52,6 +52,7 @@ struct modes_ctx {
     modes_config cfg;
     int sm_count = 148;
     uint16_t *d_lutn = nullptr;
+    uint16_t *d_lut_iq = nullptr;
     uint32_t *d_bit_syn = nullptr;
     uint32_t *d_fix_hash = nullptr;
     DeviceTables tab{};
@@ -313,7 +314,7 @@ void modes_destroy(modes_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->own_detect_stream) { cudaStreamSynchronize(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
-    cudaFree(ctx->d_lutn); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
+    cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
     if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
     delete ctx;
@@ -335,15 +336,19 @@ static int create_impl(modes_ctx *ctx) {
     std::vector<uint16_t> lutn(kNLutEntries);
     uint32_t syn[112], hash[kFixHashSlots];
     build_lutn(lutn.data());
+    std::vector<uint16_t> lut_iq(kLutIqEntries);
+    build_lut_iq(lut_iq.data());
     build_bit_syndromes(syn);
     if (!build_fix_hash(syn, hash)) return fail(nullptr, "internal: syndrome hash construction failed");
     CK(nullptr, cudaMalloc(&ctx->d_lutn, kNLutEntries * sizeof(uint16_t)));
+    CK(nullptr, cudaMalloc(&ctx->d_lut_iq, kLutIqEntries * sizeof(uint16_t)));
+    CK(nullptr, cudaMemcpy(ctx->d_lut_iq, lut_iq.data(), kLutIqEntries * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CK(nullptr, cudaMalloc(&ctx->d_bit_syn, sizeof(syn)));
     CK(nullptr, cudaMalloc(&ctx->d_fix_hash, sizeof(hash)));
     CK(nullptr, cudaMemcpy(ctx->d_lutn, lutn.data(), kNLutEntries * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CK(nullptr, cudaMemcpy(ctx->d_bit_syn, syn, sizeof(syn), cudaMemcpyHostToDevice));
     CK(nullptr, cudaMemcpy(ctx->d_fix_hash, hash, sizeof(hash), cudaMemcpyHostToDevice));
-    ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_bit_syn, ctx->d_fix_hash};
+    ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_lut_iq, ctx->d_bit_syn, ctx->d_fix_hash};
     CK(nullptr, cudaMallocHost(&ctx->pending, MODES_BUFFER_BYTES));
     for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->detect})
         if (slot_init(ctx, *s)) { g_create_error = ctx->err; return -1; }

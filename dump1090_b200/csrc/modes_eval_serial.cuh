@@ -64,18 +64,22 @@ MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) {
 // (first | second << 16) instead; words 0..7 keep the raw preamble samples.
 constexpr int kWindowWords = 121;
 
-constexpr int kIqLutEntries = 129 * 129;
+// Rows of the (|I-127|, |Q-127|) magnitude table are 136 entries (68 words) apart: consecutive rows
+// start 4 banks apart in shared memory, so the small amplitudes that most half-bit samples have
+// (|I-127|, |Q-127| < 8) spread over all 32 banks instead of piling onto two or three.
+constexpr int kIqLutStride = 136;
+constexpr int kIqLutEntries = 129 * kIqLutStride;
 
 struct Tables {
-    const uint16_t *lut_iq;      // [129*129] magnitude by (|I-127|, |Q-127|): round(sqrt(i*i+q*q)*360), dump1090.c:362
+    const uint16_t *lut_iq;      // [129 rows of kIqLutStride] magnitude by (|I-127|, |Q-127|): round(sqrt(i*i+q*q)*360), dump1090.c:362
     const uint32_t *bit_syn;     // [112]   syndrome of one flipped bit
     const uint32_t *nib_syn;     // [28*16] syndrome of nibble value x at frame nibble i: XOR of bit_syn over its set bits
     const uint32_t *fix_hash;    // [256]   inverse of bit_syn over positions 5..111
 };
 
 // Index into lut_iq of the sample held in the low (kLutLow) or high (kLutHigh) half of a word of
-// |byte - 127| values: 129 * |I-127| + |Q-127| as one byte dot product.
-constexpr uint32_t kLutLow = 0x00000181u, kLutHigh = 0x01810000u;
+// |byte - 127| values: kIqLutStride * |I-127| + |Q-127| as one byte dot product.
+constexpr uint32_t kLutLow = (uint32_t)kIqLutStride | 0x100u, kLutHigh = kLutLow << 16;
 
 // What one attempt (uncorrected, or phase corrected) yields: the six 32-bit words of a
 // modes_frame_eval (include/modes_b200.h) are made from it by eval_words().

@@ -27,9 +27,12 @@ constexpr uint32_t kBufSamples   = MODES_BUFFER_SAMPLES;
 constexpr uint32_t kScanLimit    = kBufSamples - 2;             // j < 131070
 constexpr int      kNLutEntries  = 32769;                       // magnitude by i*i+q*q
 constexpr int      kFixHashSlots = 256;
+constexpr int      kLutIqStride  = 136;                         // == serial::kIqLutStride (modes_eval_serial.cuh)
+constexpr int      kLutIqEntries = 129 * kLutIqStride;
 
 struct DeviceTables {
     const uint16_t *lutn;        // [32769] round(sqrt(n)*360), dump1090.c:362 keyed by n=i*i+q*q
+    const uint16_t *lut_iq;      // [129 x kLutIqStride] the same keyed by (|I-127|, |Q-127|); 16-byte aligned
     const uint32_t *bit_syn;     // [112] syndrome of a single flipped bit (dump1090.c:683-698 + parity bits)
     const uint32_t *fix_hash;    // [256] open-addressed inverse of bit_syn: (syndrome<<8 | pos), 0xFFFFFFFF empty
 };
@@ -65,6 +68,7 @@ void launch_eval_frames(const uint8_t *d_frames, modes_frame_eval *d_out, uint32
 
 // Host-side table construction (modes_tables.cpp).
 void build_lutn(uint16_t *out /*[32769]*/);
+void build_lut_iq(uint16_t *out /*[kLutIqEntries]*/);
 void build_bit_syndromes(uint32_t *out /*[112]*/);
 bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out /*[256]*/);
 

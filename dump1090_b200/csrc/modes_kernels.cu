@@ -834,7 +834,8 @@ constexpr int kSerWarps = 12;                          // one CTA per SM
 constexpr int kSerThreads = 32 * kSerWarps;
 constexpr int kSerRow = serial::kWindowWords;          // 121 words: odd, so lane l walking its own row hits bank 25l+k
 constexpr int kSerNibWords = 28 * 16;
-constexpr int kSerLutWords = (serial::kIqLutEntries + 3) / 4 * 2;   // even: the window area stays 8-byte aligned
+constexpr int kSerLutWords = serial::kIqLutEntries / 2;
+static_assert(serial::kIqLutStride == kLutIqStride && serial::kIqLutEntries % 8 == 0, "table geometry");
 static_assert((112 + kFixHashSlots + kSerNibWords + kSerLutWords) % 2 == 0 && (32 * kSerRow) % 2 == 0, "record staging uses 8-byte stores");
 constexpr int kSerTableWords = 112 + kFixHashSlots + kSerNibWords + kSerLutWords;
 constexpr int kSerSmemBytes = 4 * (kSerTableWords + kSerWarps * 32 * kSerRow);
@@ -842,6 +843,10 @@ constexpr int kSerSmemBytes = 4 * (kSerTableWords + kSerWarps * 32 * kSerRow);
 __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
     const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);
     return *reinterpret_cast<const uint16_t *>(p);
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_shared, const uint32_t *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 
 __global__ void __launch_bounds__(kSerThreads, 1)
@@ -853,18 +858,17 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
     uint32_t *s_win = s_nib + kSerNibWords + kSerLutWords;
     for (int i = threadIdx.x; i < 112; i += kSerThreads) s_syn[i] = tab.bit_syn[i];
     for (int i = threadIdx.x; i < kFixHashSlots; i += kSerThreads) s_hash[i] = tab.fix_hash[i];
-    // magnitude by (|I-127|, |Q-127|): the 33 KB that the per-thread lookups hit stay in shared memory
-    // (as gathers from the 64 KB table in L1 they were the kernel's bottleneck: ~5 wavefronts each)
-    for (int i = threadIdx.x; i < serial::kIqLutEntries; i += kSerThreads) {
-        const int ai = i / 129, aq = i - 129 * ai;
-        s_lut[i] = __ldg(tab.lutn + ai * ai + aq * aq);
-    }
+    // magnitude by (|I-127|, |Q-127|): the table the per-thread lookups hit stays in shared memory
+    // (as gathers from the 64 KB n-keyed table in L1 they were the kernel's bottleneck: ~5 wavefronts each)
+    for (int i = threadIdx.x; i < serial::kIqLutEntries / 8; i += kSerThreads)
+        reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(tab.lut_iq) + i);
     __syncthreads();
     for (int i = threadIdx.x; i < kSerNibWords; i += kSerThreads) s_nib[i] = serial::nibble_syndrome(s_syn, i >> 4, i & 15);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wwin = s_win + warp * 32 * kSerRow;
+    const uint32_t wwin_s = (uint32_t)__cvta_generic_to_shared(wwin);
     const serial::Tables T{s_lut, s_syn, s_nib, s_hash};
     uint32_t n_cand = counters[0];
     if (n_cand > cand_capacity) n_cand = cand_capacity;
@@ -882,17 +886,17 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
 
         // stage the windows: row c = candidate c, words (first>>1) .. +120 of the body
         if (__all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples)) {
-            // common case (no window in the carry block): branch-free, four rows in flight
-#pragma unroll 4
+            // common case (no window in the carry block): asynchronous copies straight into shared
+            // memory, all 32 rows in flight, one wait
+#pragma unroll 8
             for (int c = 0; c < 32; c++) {
                 const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
-                const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
-                uint32_t *row = wwin + c * kSerRow;
-                const uint32_t w0 = __ldg(wp + lane), w1 = __ldg(wp + 32 + lane), w2 = __ldg(wp + 64 + lane);
-                const uint32_t w3 = lane < serial::kWindowWords - 96 ? __ldg(wp + 96 + lane) : 0u;
-                row[lane] = w0; row[32 + lane] = w1; row[64 + lane] = w2;
-                if (lane < serial::kWindowWords - 96) row[96 + lane] = w3;
+                const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1) + lane;
+                const uint32_t dst = wwin_s + 4u * (uint32_t)(c * kSerRow + lane);
+                cp_async4(dst, wp); cp_async4(dst + 128u, wp + 32); cp_async4(dst + 256u, wp + 64);
+                if (lane < serial::kWindowWords - 96) cp_async4(dst + 384u, wp + 96);
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
         } else {
             for (uint32_t c = 0; c < n; c++) {
                 const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);

@@ -2,6 +2,8 @@
 // kernels read.  Generated from their defining formulas, never copied:
 //   lutn     magnitude by squared amplitude: the reference's
 //            round(sqrt(i*i+q*q)*360) (dump1090.c:362) keyed by n = i*i+q*q
+//   lut_iq   the same magnitude keyed by (|I-127|, |Q-127|), rows kLutIqStride apart (the
+//            frame-evaluation kernel keeps it in shared memory)
 //   bit_syn  syndrome of one flipped bit at frame position p of a 112-bit frame:
 //            x^(111-p) mod the Mode S generator 0x1FFF409 for data bits (what
 //            modes_checksum_table holds, dump1090.c:683-698), the bit itself for
@@ -16,6 +18,12 @@ namespace modes {
 
 void build_lutn(uint16_t *out) {
     for (int n = 0; n < kNLutEntries; n++) out[n] = (uint16_t)std::round(std::sqrt((double)n) * 360);
+}
+
+void build_lut_iq(uint16_t *out) {
+    std::memset(out, 0, sizeof(uint16_t) * kLutIqEntries);
+    for (int i = 0; i <= 128; i++)
+        for (int q = 0; q <= 128; q++) out[i * kLutIqStride + q] = (uint16_t)std::round(std::sqrt((double)(i * i + q * q)) * 360);
 }
 
 void build_bit_syndromes(uint32_t *out) {

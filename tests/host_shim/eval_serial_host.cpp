@@ -9,6 +9,7 @@
 
 namespace modes {
 void build_lutn(uint16_t *out);
+void build_lut_iq(uint16_t *out);
 void build_bit_syndromes(uint32_t *out);
 bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out);
 }
@@ -17,19 +18,16 @@ bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out);
 extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samples, const uint32_t *cand_v, uint32_t n,
                                     int fix_errors, int aggressive, modes_candidate *out) {
     using namespace modes::serial;
-    static std::vector<uint16_t> lutn(32769);
     static uint32_t bit_syn[112], fix_hash[256];
     static std::vector<uint32_t> nib_syn(28 * 16);
     static std::vector<uint16_t> lut_iq(kIqLutEntries);
     static bool ready = false;
     if (!ready) {
-        modes::build_lutn(lutn.data());
         modes::build_bit_syndromes(bit_syn);
         if (!modes::build_fix_hash(bit_syn, fix_hash)) return -1;
         for (int pos = 0; pos < 28; pos++)
             for (uint32_t v = 0; v < 16; v++) nib_syn[pos * 16 + v] = nibble_syndrome(bit_syn, pos, v);
-        for (int i = 0; i <= 128; i++)
-            for (int q = 0; q <= 128; q++) lut_iq[i * 129 + q] = lutn[i * i + q * q];
+        modes::build_lut_iq(lut_iq.data());
         ready = true;
     }
     const Tables tab{lut_iq.data(), bit_syn, nib_syn.data(), fix_hash};
