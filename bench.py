@@ -165,6 +165,11 @@ def run_ours(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    numa = {"numa_node": None}
+    if os.environ.get("BENCH_NUMA_BIND", "1") != "0":
+        numa = sharded.bind_near_gpu(local_rank)              # before any pinned allocation
+    if os.environ.get("BENCH_E2E_TRACE"):
+        print(f"rank {rank}: numa binding {numa}", file=sys.stderr)
 
     capture, what = load_capture()
     nbuf = GIB // api.BUFFER_BYTES
@@ -269,32 +274,70 @@ def run_ours(args) -> None:
         worker = [None]
         result = [0]
 
+        trace = os.environ.get("BENCH_E2E_TRACE") and rank == 0
+        tr = []
+        h2d_ms = []
+
         def resolve_async(k):
+            t0 = time.perf_counter()
             shards = [(c, t, plan[r][0]) for r, (c, t) in enumerate(pg.fetch(k))]
+            t1 = time.perf_counter()
             resolver.rearm_output()
             resolver.reset_state()
             resolver.run_shards(shards)
             result[0] = resolver.output_count()
+            if trace:
+                tr.append(("worker", round(1e3 * (t1 - t0), 2), round(1e3 * (time.perf_counter() - t1), 2)))
+
+        # one resolver thread for the whole run, fed step numbers through a queue
+        import queue
+        jobs, done = queue.Queue(), queue.Queue()
+
+        def resolver_loop():
+            while True:
+                k = jobs.get()
+                if k is None:
+                    return
+                try:
+                    resolve_async(k)
+                    done.put(None)
+                except BaseException as e:                   # surface it in e2e_join()
+                    done.put(e)
+
+        if rank == 0:
+            threading.Thread(target=resolver_loop, daemon=True).start()
 
         def e2e_join():
             if worker[0] is not None:
-                worker[0].join()
                 worker[0] = None
+                err = done.get()
+                if err is not None:
+                    raise err
             return result[0]
 
         def e2e_step():
             k = e2e_no[0] & 1
             e2e_no[0] += 1
+            t0 = time.perf_counter()
             pg.detect_host(dec, pinned.ptr, nbuf, carry, k)
             dec.detect_wait()
+            t1 = time.perf_counter()
+            h2d_ms.append(1e3 * (t1 - t0))
             pg.fence().wait()
             torch.cuda.synchronize(dev)
+            t2 = time.perf_counter()
             if rank == 0:
                 e2e_join()                                  # step i-1 resolved (its buffer is k^1)
-                worker[0] = threading.Thread(target=resolve_async, args=(k,))
-                worker[0].start()
+                t3 = time.perf_counter()
+                worker[0] = k
+                jobs.put(k)
+            else:
+                t3 = t2
             if world > 1:
                 dist.barrier()                              # nobody overwrites buffer k^1... see note
+            if trace:
+                tr.append(("step", round(1e3 * (t1 - t0), 2), round(1e3 * (t2 - t1), 2), round(1e3 * (t3 - t2), 2),
+                           round(1e3 * (time.perf_counter() - t3), 2)))
             return result[0]
 
     with torch.cuda.stream(stream):
@@ -316,6 +359,12 @@ def run_ours(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_value = world * SAMPLES_PER_GIB * e2e_steps / e2e_s / 1e6
+    if world > 1 and os.environ.get("BENCH_E2E_TRACE"):
+        print(f"rank {rank}: upload+kernels per step, ms: min {min(h2d_ms):.1f} median {sorted(h2d_ms)[len(h2d_ms) // 2]:.1f}", file=sys.stderr)
+    if world > 1 and rank == 0 and os.environ.get("BENCH_E2E_TRACE"):
+        print("e2e trace (ms): step = (h2d+kernels, fence+sync, join, barrier), worker = (fetch, resolve)", file=sys.stderr)
+        for row in tr[-24:]:
+            print("  ", row, file=sys.stderr)
     d2h = n_cand * 56 + api.tiles_for(nbuf) * 8 + 16
 
     clocks = sampler.stop() if rank == 0 else None

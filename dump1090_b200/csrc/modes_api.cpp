@@ -66,6 +66,7 @@ struct modes_ctx {
     int64_t buffers_done = 0;
     bool finished = false;
     ResolveState rs;
+    ResolveScratch *scratch = nullptr;
     MessageOut out;                       // modes_set_sink / modes_set_output
     cudaStream_t own_detect_stream = nullptr;
     std::string err;
@@ -259,7 +260,7 @@ int collect(modes_ctx *ctx, Slot &s) {
     CK(ctx, cudaStreamSynchronize(s.stream));
     const double t2 = dbg ? now_ms() : 0;
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
-    resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->out);
+    resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->out, ctx->scratch);
     if (dbg) fprintf(stderr, "[collect] %zu buffers, %llu cands: wait %.3f ms, d2h %.3f ms, resolve %.3f ms (t=%.3f)\n",
                      s.n_buffers, (unsigned long long)n, t1 - t0, t2 - t1, now_ms() - t2, now_ms());
     return 0;
@@ -317,6 +318,7 @@ void modes_destroy(modes_ctx *ctx) {
     cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
     if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
+    scratch_destroy(ctx->scratch);
     delete ctx;
 }
 
@@ -332,6 +334,8 @@ static int create_impl(modes_ctx *ctx) {
     CK(nullptr, cudaGetDeviceProperties(&prop, ctx->cfg.device));
     if (prop.major < 10) return fail(nullptr, "device %d is sm_%d%d; kernels are built for sm_100a only", ctx->cfg.device, prop.major, prop.minor);
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->scratch = scratch_create();
+    if (!ctx->scratch) return fail(nullptr, "out of memory");
 
     std::vector<uint16_t> lutn(kNLutEntries);
     uint32_t syn[112], hash[kFixHashSlots];
@@ -507,11 +511,11 @@ int modes_resolve(modes_ctx *ctx, const modes_candidate *candidates, const modes
                   int64_t buffer_base) {
     if (!ctx || !tiles) return -1;
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
-    resolve_candidates(ctx->rs, rc, candidates, tiles, n_tiles, buffer_base, ctx->out);
+    resolve_candidates(ctx->rs, rc, candidates, tiles, n_tiles, buffer_base, ctx->out, ctx->scratch);
     return 0;
 }
 
-struct modes_resolver { ResolveState rs; ResolveConfig rc; MessageOut out; };
+struct modes_resolver { ResolveState rs; ResolveConfig rc; MessageOut out; ResolveScratch *scratch = nullptr; };
 
 modes_resolver *modes_resolver_create(const modes_config *cfg) {
     modes_resolver *r = new (std::nothrow) modes_resolver();
@@ -520,16 +524,18 @@ modes_resolver *modes_resolver_create(const modes_config *cfg) {
     if (cfg) c = *cfg; else modes_default_config(&c);
     r->rc = ResolveConfig{c.fix_errors, c.aggressive, c.check_crc};
     r->rs.reset();
+    r->scratch = scratch_create();
+    if (!r->scratch) { delete r; return nullptr; }
     return r;
 }
 
-void modes_resolver_destroy(modes_resolver *r) { delete r; }
+void modes_resolver_destroy(modes_resolver *r) { if (r) { scratch_destroy(r->scratch); delete r; } }
 
 int modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
                        size_t n_tiles, int64_t buffer_base, modes_sink_fn sink, void *user) {
     if (!r || !tiles) return -1;
     r->out.sink = sink; r->out.user = user;
-    resolve_candidates(r->rs, r->rc, candidates, tiles, n_tiles, buffer_base, r->out);
+    resolve_candidates(r->rs, r->rc, candidates, tiles, n_tiles, buffer_base, r->out, r->scratch);
     return 0;
 }
 
@@ -538,7 +544,7 @@ int modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_ca
                               modes_sink_fn sink, void *user) {
     if (!r || (n_shards && (!candidates || !tiles || !n_tiles || !buffer_base))) return -1;
     r->out.sink = sink; r->out.user = user;
-    resolve_shards(r->rs, r->rc, n_shards, candidates, tiles, n_tiles, buffer_base, r->out);
+    resolve_shards(r->rs, r->rc, n_shards, candidates, tiles, n_tiles, buffer_base, r->out, r->scratch);
     return 0;
 }
 

@@ -90,11 +90,19 @@ struct MessageOut {
     modes_message *array = nullptr; size_t capacity = 0; size_t count = 0;
 };
 
+// Working memory of the resolve (verdict lists, per-shard runs), owned by a context / resolver and
+// kept between calls: grown once, never handed back (re-faulting ~14 MB of verdicts per GiB in every
+// call costs more than the verdicts themselves).
+struct ResolveScratch;
+ResolveScratch *scratch_create();
+void scratch_destroy(ResolveScratch *s);
+
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
-                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out);
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out,
+                        ResolveScratch *scratch);
 void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
                     const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
-                    MessageOut &out);
+                    MessageOut &out, ResolveScratch *scratch);
 // The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
 int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
 

@@ -22,6 +22,7 @@
 #include <ctime>
 #include <functional>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 #include "modes_internal.h"
@@ -271,7 +272,18 @@ static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const mod
 // The verdict pass over one run of tiles: everything order-dependent, no message structs yet.
 static void judge_tiles(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
                         size_t n_tiles, int64_t buffer_base, std::vector<Delivery> &deliveries) {
+    // The kernels append a tile's records wherever the global cursor stands when the tile finishes:
+    // records are contiguous per tile but the tiles lie scattered through the array, so walking them
+    // in stream order is a chain of cache misses (the records were just written by DMA).  Request
+    // the lines of a tile well before it is reached.
+    constexpr size_t kAhead = 24;
+    static const bool no_pf = std::getenv("MODES_NO_PREFETCH") != nullptr;
     for (size_t ti = 0; ti < n_tiles; ti++) {
+        if (!no_pf && ti + kAhead < n_tiles && tiles[ti + kAhead].count) {
+            const char *p = reinterpret_cast<const char *>(cands + tiles[ti + kAhead].offset);
+            const size_t bytes = (size_t)tiles[ti + kAhead].count * sizeof(modes_candidate);
+            for (size_t o = 0; o < bytes && o < 512; o += 64) __builtin_prefetch(p + o, 0, 1);
+        }
         const modes_candidate *c = cands + tiles[ti].offset;
         for (uint32_t k = 0; k < tiles[ti].count; k++, c++) {
             const int64_t buffer = buffer_base + (c->t >> 17);
@@ -315,9 +327,15 @@ static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
     out.count += n;
 }
 
+struct ShardRun { ResolveState start, end; std::vector<Delivery> deliveries; };
+struct ResolveScratch { std::vector<Delivery> deliveries; std::vector<ShardRun> runs; };
+ResolveScratch *scratch_create() { return new (std::nothrow) ResolveScratch(); }
+void scratch_destroy(ResolveScratch *s) { delete s; }
+
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
-                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out) {
-    static thread_local std::vector<Delivery> deliveries;
+                        const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out,
+                        ResolveScratch *scratch) {
+    std::vector<Delivery> &deliveries = scratch->deliveries;
     deliveries.clear();
     static const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
     const auto t0 = std::chrono::steady_clock::now();
@@ -334,20 +352,19 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
 //
 // The only state that crosses a shard boundary is the ICAO address cache (skip state restarts at
 // every reference buffer, and shards are whole buffers).  Shard k is therefore resolved from a
-// GUESS of the cache at its start — the cache shard k-1 ended with in the previous round — and the
-// guess is verified afterwards against the cache shard k-1 really ended with.  A shard whose guess
-// was wrong is simply resolved again.  A long shard overwrites every one of the 1024 slots many
-// times, so its final cache hardly ever depends on its initial one and two rounds normally
-// suffice; in the worst case the loop degenerates to the sequential order, never to a wrong result.
+// GUESS of the cache at its start — first the call's starting cache overwritten by the tail of
+// shard k-1, in later rounds the cache shard k-1 ended with in the previous round — and the guess
+// is verified afterwards against the cache shard k-1 really ended with.  A shard whose guess was
+// wrong is simply resolved again.  One round normally suffices; in the worst case the loop
+// degenerates to the sequential order, never to a wrong result.
 void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
                     const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
-                    MessageOut &out) {
+                    MessageOut &out, ResolveScratch *scratch) {
     // Delivery lists keep their capacity from call to call (growing them from nothing in every
     // call costs more in page faults, taken concurrently by the shard threads, than the verdicts).
-    struct Run { ResolveState start, end; std::vector<Delivery> deliveries; };
-    static thread_local std::vector<Run> run_store;
-    if (run_store.size() < n_shards) run_store.resize(n_shards);
-    Run *const runs = run_store.data();                    // the shard threads must see THIS thread's store
+    using Run = ShardRun;
+    if (scratch->runs.size() < n_shards) scratch->runs.resize(n_shards);
+    Run *const runs = scratch->runs.data();
     ResolveState blank;
     blank.reset();
     auto run_shard = [&](size_t k, const ResolveState &from) {
@@ -360,7 +377,7 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
         judge_tiles(r.end, cfg, cands[k], tiles[k], n_tiles[k], buffer_base[k], r.deliveries);
         if (std::getenv("MODES_RESOLVE_TIMING2")) std::fprintf(stderr, "  shard %zu: %.2f ms\n", k, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };
-    static const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
+    const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t_start = now();
     int rounds = 0;
@@ -374,8 +391,27 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
             rerun[k] = round == 0 || k == done || std::memcmp(guess[k].icao, runs[k].start.icao, sizeof(blank.icao)) != 0;
         }
         std::vector<std::thread> th;
-        for (size_t k = done; k < n_shards; k++)
-            if (rerun[k]) th.emplace_back([&, k] { run_shard(k, guess[k]); });
+        for (size_t k = done; k < n_shards; k++) {
+            if (!rerun[k]) continue;
+            if (round == 0 && k > done) {
+                // First guess: the cache this call started with, overwritten by what the LAST SIXTEENTH of
+                // shard k-1 writes (addresses are re-confirmed every second or so, so the tail of a long
+                // shard has normally written every slot the whole shard leaves changed).
+                th.emplace_back([&, k] {
+                    ResolveState g = st;
+                    g.cur_buffer = -1; g.next_j = 0;
+                    const size_t nt = n_tiles[k - 1];
+                    size_t tail = nt / 16 > 256 ? nt / 16 : 256;
+                    if (tail > nt) tail = nt;
+                    runs[k].deliveries.clear();
+                    judge_tiles(g, cfg, cands[k - 1], tiles[k - 1] + (nt - tail), tail, buffer_base[k - 1], runs[k].deliveries);
+                    g.cur_buffer = -1; g.next_j = 0;
+                    run_shard(k, g);
+                });
+            } else {
+                th.emplace_back([&, k] { run_shard(k, guess[k]); });
+            }
+        }
         for (auto &t : th) t.join();
         // accept the longest verified prefix
         for (; done < n_shards; done++) {

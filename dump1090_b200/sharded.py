@@ -111,6 +111,36 @@ def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):
     return w1, w2
 
 
+def bind_near_gpu(device_index: int) -> dict:
+    """Pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that the pinned
+    host buffers it allocates next are local to that GPU's PCIe root (a rank whose buffers sit on
+    the other socket uploads at a fraction of the link rate, and a sharded step is as slow as its
+    slowest rank).  Best effort: returns what it did, never raises."""
+    import os
+    info = {"numa_node": None, "cpus": None}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["cpus"] = len(allowed)
+    except Exception as e:                                    # no sysfs, no permission, ...: stay unbound
+        info["error"] = repr(e)
+    return info
+
+
 class PeerGather:
     """Record gather fused into the kernels: every rank's scan / frame-evaluation kernels store
     their tile table and candidate records straight into a buffer in rank 0's HBM (mapped through

@@ -7,9 +7,13 @@ timeout 400 python bench.py > gpurun_out/bench_n1_$tag.json 2> gpurun_out/bench_
 cat gpurun_out/bench_n1_$tag.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$tag.csv \
     python bench.py --steps 3 --warmup 3 > gpurun_out/ncu_bench_$tag.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"scan_kernel|eval_kernel" -s 2 -c 2 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"scan_kernel|eval_serial_kernel" -s 2 -c 2 \
     -f -o gpurun_out/prof_r1$tag python scripts/ncu_target.py > gpurun_out/ncu_full_$tag.log 2>&1
 tail -2 gpurun_out/ncu_full_$tag.log
+for tool in memcheck racecheck; do
+  timeout 200 compute-sanitizer --tool $tool python scripts/sanitize_target.py > gpurun_out/sanitizer_${tool}_$tag.log 2>&1
+  tail -3 gpurun_out/sanitizer_${tool}_$tag.log
+done
 if [ -n "$2" ]; then
   for t in 1 8 16 32; do
     echo "== MODES_BUILD_THREADS=$t"

@@ -23,11 +23,23 @@ cnt = np.bincount(g, minlength=n_tiles).astype(np.uint32)
 off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint32)
 tiles = np.zeros(n_tiles, dtype=api.TILE_DTYPE)
 tiles["offset"] = off; tiles["count"] = cnt
+if len(sys.argv) > 3 and sys.argv[3] == "scatter":
+    # the GPU appends tiles in completion order: scatter the tiles' record runs through the array
+    rng = np.random.default_rng(5)
+    order = np.argsort(np.arange(n_tiles) + rng.integers(0, 6000, n_tiles))      # locally scrambled, globally increasing
+    new_off = np.zeros(n_tiles, dtype=np.uint32)
+    new_off[order] = np.concatenate([[0], np.cumsum(cnt[order])[:-1]])
+    src = np.repeat(off, cnt) + (np.arange(len(arr)) - np.repeat(off, cnt))
+    dst = np.repeat(new_off, cnt) + (np.arange(len(arr)) - np.repeat(off, cnt))
+    scattered = np.zeros_like(arr)
+    scattered.view(np.uint8).reshape(-1, 56)[dst] = arr.view(np.uint8).reshape(-1, 56)[src]
+    arr = scattered
+    tiles["offset"] = new_off
 
 for shards in (1, n_sh):
     r = api.Resolver(fix_errors=0, aggressive=0, check_crc=1)
     out = r.set_output_array(shards * 600_000 * mib // 1024 + 1000)
-    sh = [(arr, tiles, k * n_buf) for k in range(shards)]
+    sh = [(arr.copy(), tiles.copy(), k * n_buf) for k in range(shards)]          # distinct memory per shard
     best = 1e9
     for it in range(3):
         r.reset_state(); r.rearm_output()

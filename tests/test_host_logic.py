@@ -131,3 +131,48 @@ def test_parallel_shard_resolve_is_exact(nshards, checker_libs):
     t2 = np.array([(0, a2.size)], dtype=api.TILE_DTYPE)
     seq.run(a2, t2, buffer_base=nbuf); par.run(a2, t2, buffer_base=nbuf)
     assert [m.raw_line() for m in par.take_messages()] == [m.raw_line() for m in seq.take_messages()]
+
+
+def test_parallel_shard_resolve_recovers_from_a_wrong_guess(checker_libs, capfd, monkeypatch):
+    """The first guess of a shard's starting ICAO cache comes from the tail of the previous shard.
+    An address announced only early in shard 0 is missing from that guess; a DF4 reply from it in
+    shard 1 is then judged wrongly, the verification catches it, and the shard is resolved again."""
+    from dump1090_b200 import sharded
+    nbuf = 24
+    n = 131072 * nbuf
+    me = bytes([0x58, 0xC3, 0x82, 0xD6, 0x90, 0xC8, 0xAC])               # an airborne-position ME field
+    a, b = 0x4840D6, 0x3C6444
+    frames = [(131072 + 5000, synth.make_frame(17, 5, a.to_bytes(3, "big") + me), 80.0, 0.3, 0.0)]   # A: once, early
+    for k in range(nbuf):                                                 # B: all along
+        frames.append((131072 * k + 40000, synth.make_frame(17, 5, b.to_bytes(3, "big") + me), 70.0, 1.1, 0.0))
+    frames.append((131072 * 14 + 9000, synth.make_frame(4, 0, bytes([0x01, 0x85, 0x10]), icao_for_ap=a), 75.0, 0.7, 0.0))
+    frames.append((131072 * 20 + 9000, synth.make_frame(5, 0, bytes([0x02, 0x20, 0x31]), icao_for_ap=b), 75.0, 0.2, 0.0))
+    data = synth.synth_stream(n, frames, seed=9)
+    cands = C.oracle_scan_candidates(data)
+    arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE)
+
+    def tiled(sel, n_buffers):                                            # one tile per 4096 positions, like the scan kernel
+        g = (sel["t"] + 2) // 4096
+        nt = api.tiles_for(n_buffers)
+        cnt = np.bincount(g, minlength=nt).astype(np.uint32)
+        t = np.zeros(nt, dtype=api.TILE_DTYPE)
+        t["count"] = cnt
+        t["offset"] = np.concatenate([[0], np.cumsum(cnt)[:-1]])
+        return t
+
+    seq = api.Resolver()
+    seq.run(arr, tiled(arr, nbuf + 1))
+    want = [C.msg_fields(m, with_pos=True) for m in seq.take_messages()]
+    assert any(m["msgtype"] == 4 for m in want) and any(m["msgtype"] == 5 for m in want)
+    shards = []
+    for first, count in sharded.shard_plan(nbuf, 2):
+        sel = arr[((arr["t"] >> 17) >= first) & ((arr["t"] >> 17) < first + count)].copy()
+        sel["t"] -= first << 17
+        shards.append((sel, tiled(sel, count), first))
+    monkeypatch.setenv("MODES_RESOLVE_TIMING", "1")
+    par = api.Resolver()
+    capfd.readouterr()
+    par.run_shards(shards)
+    assert "2 rounds" in capfd.readouterr().err                           # the guess was wrong, and noticed
+    assert [C.msg_fields(m, with_pos=True) for m in par.take_messages()] == want
+    assert par.stats() == seq.stats()
