@@ -277,9 +277,8 @@ static void judge_tiles(ResolveState &st, const ResolveConfig &cfg, const modes_
     // in stream order is a chain of cache misses (the records were just written by DMA).  Request
     // the lines of a tile well before it is reached.
     constexpr size_t kAhead = 24;
-    static const bool no_pf = std::getenv("MODES_NO_PREFETCH") != nullptr;
     for (size_t ti = 0; ti < n_tiles; ti++) {
-        if (!no_pf && ti + kAhead < n_tiles && tiles[ti + kAhead].count) {
+        if (ti + kAhead < n_tiles && tiles[ti + kAhead].count) {
             const char *p = reinterpret_cast<const char *>(cands + tiles[ti + kAhead].offset);
             const size_t bytes = (size_t)tiles[ti + kAhead].count * sizeof(modes_candidate);
             for (size_t o = 0; o < bytes && o < 512; o += 64) __builtin_prefetch(p + o, 0, 1);
@@ -373,9 +372,7 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
         std::memset(r.start.stats, 0, sizeof(r.start.stats));
         r.end = r.start;
         r.deliveries.clear();
-        const auto t0 = std::chrono::steady_clock::now();
         judge_tiles(r.end, cfg, cands[k], tiles[k], n_tiles[k], buffer_base[k], r.deliveries);
-        if (std::getenv("MODES_RESOLVE_TIMING2")) std::fprintf(stderr, "  shard %zu: %.2f ms\n", k, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };
     const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };

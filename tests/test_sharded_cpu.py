@@ -77,3 +77,15 @@ def test_shard_plan_and_carry():
     assert sharded.carry_before(stream, 0) is None
     c = sharded.carry_before(stream, 2)
     assert len(c) == api.CARRY_BYTES and c == bytes(stream[2 * api.BUFFER_BYTES - api.CARRY_BYTES: 2 * api.BUFFER_BYTES])
+
+
+def test_bind_near_gpu_is_best_effort():
+    """No GPU (or no sysfs entry) must not raise: the helper reports and leaves the affinity alone."""
+    import os
+    from dump1090_b200 import sharded
+    before = os.sched_getaffinity(0)
+    info = sharded.bind_near_gpu(0)
+    assert "numa_node" in info and "cpus" in info
+    import torch
+    if not torch.cuda.is_available():
+        assert info["cpus"] is None and os.sched_getaffinity(0) == before
