@@ -395,6 +395,16 @@ def run_ours(args) -> None:
                             "kind": kind,
                             "sample": "first 512 MiB of the workload x 3 loops, single thread (the reference's "
                                       "own design: one decode thread), --no-fix"}
+            if kind == "reference":
+                try:                                    # the two hot calls separately; never fatal
+                    part = sample[: 256 << 20]
+                    t_mag, t_det = checker.ref_time_phases(part, fix=0, loops=1)
+                    n = part.size // 2
+                    cpu_baseline["phases"] = {"computeMagnitudeVector_Msamples_s": round(n / t_mag / 1e6, 1),
+                                              "detectModeS_Msamples_s": round(n / t_det / 1e6, 1),
+                                              "sample": "first 256 MiB, one pass"}
+                except Exception as e:
+                    cpu_baseline["phases"] = {"error": repr(e)}
 
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world,

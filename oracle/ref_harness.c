@@ -158,6 +158,37 @@ double ref_time_decode(const unsigned char *iq, size_t nbytes, int fix_errors, i
     return (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
 }
 
+/* ctypes entry: the same loop with the two hot calls timed separately (report
+ * computeMagnitudeVector and detectModeS separately and combined).  seconds[0] = magnitude,
+ * seconds[1] = detectModeS, summed over all buffers of `loops` passes. */
+void ref_time_phases(const unsigned char *iq, size_t nbytes, int fix_errors, int aggressive,
+                     int check_crc, int loops, double seconds[2]) {
+    struct timespec a, b, c;
+    ref_reset(fix_errors, aggressive, check_crc, 1);
+    g_out = NULL; g_print = 0;
+    seconds[0] = seconds[1] = 0;
+    for (int i = 0; i < loops; i++) {
+        size_t off = 0;
+        for (;;) {                                                   /* ref_feed, instrumented */
+            size_t avail = nbytes - off;
+            size_t take = avail < MODES_DATA_LEN ? avail : MODES_DATA_LEN;
+            int eof = take < MODES_DATA_LEN;
+            memcpy(Modes.data, Modes.data + MODES_DATA_LEN, (MODES_FULL_LEN - 1) * 4);
+            memcpy(Modes.data + (MODES_FULL_LEN - 1) * 4, iq + off, take);
+            if (eof) memset(Modes.data + (MODES_FULL_LEN - 1) * 4 + take, 127, MODES_DATA_LEN - take);
+            off += take;
+            clock_gettime(CLOCK_MONOTONIC, &a);
+            computeMagnitudeVector();
+            clock_gettime(CLOCK_MONOTONIC, &b);
+            detectModeS(Modes.magnitude, Modes.data_len / 2);
+            clock_gettime(CLOCK_MONOTONIC, &c);
+            seconds[0] += (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+            seconds[1] += (c.tv_sec - b.tv_sec) + 1e-9 * (c.tv_nsec - b.tv_nsec);
+            if (eof) break;
+        }
+    }
+}
+
 /* ctypes entry: the two reference kernels on one caller-supplied buffer image
  * (262620 bytes, carry included) — lets tests pin the magnitude vector. */
 void ref_magnitude(const unsigned char *data262620, uint16_t *mag131310) {

@@ -189,6 +189,17 @@ def ref_time(data, **kw):
     return _time(ref_lib(), "ref_time_decode", data, **kw)
 
 
+def ref_time_phases(data, fix=1, aggressive=0, check_crc=1, loops=1):
+    """(seconds in computeMagnitudeVector, seconds in detectModeS) of the unmodified reference."""
+    a = _as_u8(data)
+    fn = ref_lib().ref_time_phases
+    fn.restype = None
+    out = (ctypes.c_double * 2)()
+    fn(a.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(a.size), int(fix), int(aggressive), int(check_crc),
+       int(loops), out)
+    return float(out[0]), float(out[1])
+
+
 def modes1_path() -> Path:
     """The reference's sample capture (testfiles/modes1.bin).  `make -C oracle ref`
     copies it to oracle/_ref/ (git-ignored, shipped to the GPU box)."""
