@@ -949,10 +949,13 @@ void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs
                                                               records, fix_errors, aggressive);
         return;
     }
-    static const bool configured = [] {
-        return cudaFuncSetAttribute(eval_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes) == cudaSuccess;
-    }();
-    (void)configured;
+    // the opt-in to > 48 KB of dynamic shared memory is per device
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaFuncSetAttribute(eval_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes);
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
     eval_serial_kernel<<<sm_count, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
                                                                             scan.cand_capacity, records, fix_errors, aggressive);
 }
