@@ -30,8 +30,21 @@ MODES_SERIAL_FN uint32_t bitrev(uint32_t x) { return __brev(x); }
 // (hi:lo) >> s for s in {16, 32}
 MODES_SERIAL_FN uint32_t funnel(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }
 MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return __byte_perm(x, 0u, 0x0123u); }
+MODES_SERIAL_FN uint32_t absdiff_add(uint32_t a, uint32_t b, uint32_t c) { return __usad(a, b, c); }   // |a-b| + c
+MODES_SERIAL_FN uint32_t perm(uint32_t x, uint32_t sel) { return __byte_perm(x, 0u, sel); }             // bytes of x picked by sel's nibbles
+MODES_SERIAL_FN uint32_t opaque(uint32_t x) { asm volatile("" : "+r"(x)); return x; }                    // keep a value in its register
 #else
 MODES_SERIAL_FN uint32_t bswap(uint32_t x) { return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24); }
+MODES_SERIAL_FN uint32_t absdiff_add(uint32_t a, uint32_t b, uint32_t c) { return (a > b ? a - b : b - a) + c; }
+MODES_SERIAL_FN uint32_t perm(uint32_t x, uint32_t sel) {
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) {
+        const uint32_t n = (sel >> (4 * k)) & 7u;
+        r |= (n < 4 ? (x >> (8 * n)) & 0xffu : 0u) << (8 * k);
+    }
+    return r;
+}
+MODES_SERIAL_FN uint32_t opaque(uint32_t x) { return x; }
 MODES_SERIAL_FN uint32_t absdiff127x4(uint32_t w) {
     uint32_t r = 0;
     for (int k = 0; k < 4; k++) {
@@ -267,6 +280,70 @@ MODES_SERIAL_FN void correct_slice_block(const uint32_t *p, int step, bool fwd, 
     }
 }
 
+// Leaner code for the same first-pass block (|lo - hi| as one VABSDIFF; 18.7 instead of 24.6
+// instructions per bit).  First pass, block k: raw samples -> magnitude pairs (stored back into the window) -> sliced
+// bits (dump1090.c:1667-1690); accumulates the delta sums (:1692-1693).
+MODES_SERIAL_FN uint32_t first_pass_block_lean(uint32_t *win, int k, uint32_t shift, const uint16_t *lut_iq, uint32_t &wa,
+                                          uint32_t &prev, uint32_t &dsum, uint32_t &d56) {
+    uint32_t f = 0;
+    uint32_t *p = win + 8 + 16 * k;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t wb = p[i + 1];
+        const uint32_t a = absdiff127x4(funnel(wa, wb, shift));
+        wa = wb;
+        const uint32_t lo = lut_iq[dot4(a, kLutLow)];
+        const uint32_t hi = lut_iq[dot4(a, kLutHigh)];
+        p[i] = lo | (hi << 16);
+        const uint32_t d = absdiff_add(lo, hi, 0u);
+        dsum += d;
+        if (i == 7 && k == 3) d56 = dsum;                                      // bits 0..55 (:1716)
+        bool definite = d >= 256u;
+        if (i == 0) definite = definite || k == 0;                             // bit 0 is always taken (:1675)
+        prev = definite ? (uint32_t)(lo > hi) : prev;
+        f |= prev << i;
+    }
+    return f;
+}
+
+// Leaner code for the same block (20.3 instead of 24.8 instructions per bit).
+// Phase correction (dump1090.c:1498-1558) and slicing of the corrected samples, one block of 16
+// bits walking from *p in direction `step` (+1 forwards along the frame, -1 backwards): the
+// half-bit sample next to the previous decision is rescaled by f_one or f_zero according to that
+// decision, then the corrected pair is classified like the first pass (:1675): `d16` collects the
+// definite bits, `o16` the definite ones, both in walk order.  `end0` / `end15` say that the
+// first / last bit of the block is bit 0 of the frame (always definite; a tie there is the
+// tri-state of :1681).
+//
+// Written on integer masks rather than bools (all-ones = true): with sixteen unrolled steps the
+// compiler otherwise shuttles the conditions between predicates and registers (7 SEL per bit).
+//   sel_x / sel_y  byte selectors that extract the rescaled / the other half of a pair, zero-extended
+//   dir            0 forwards, ~0 backwards;   f_pick = f_one ^ f_zero
+//   not_e          ~0 unless the previous decision was "one"
+MODES_SERIAL_FN void correct_slice_block_lean(const uint32_t *p, int step, uint32_t sel_x, uint32_t sel_y, uint32_t dir,
+                                         bool end0, bool end15, uint32_t f_one, uint32_t f_pick, uint32_t &not_e,
+                                         uint32_t &d16, uint32_t &o16, uint32_t &tie0) {
+    uint32_t nd = 0, no = 0;                               // complements of d16 / o16, built by OR
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const uint32_t m = p[i * step];
+        const uint32_t x = perm(m, sel_x), y = perm(m, sel_y);
+        const uint32_t xs = scale_sample(x, f_one ^ (not_e & f_pick));          // previous one: f_one, else f_zero
+        const int32_t s = (int32_t)(xs - y);
+        // "one" = first corrected sample > second: forwards s > 0, backwards s < 0.
+        // u = forwards s-1, backwards ~s: one <=> u >= 0
+        const int32_t u = (int32_t)(((uint32_t)s ^ dir) + ~dir);
+        not_e = (uint32_t)(u >> 31);
+        uint32_t not_def = (uint32_t)((int32_t)(absdiff_add(xs, y, 0u) - 256u) >> 31);   // ~0 when |delta| < 256
+        if (i == 0 && end0) { not_def = 0; tie0 = (uint32_t)(s == 0); }
+        if (i == 15 && end15) { not_def = 0; tie0 = (uint32_t)(s == 0); }
+        nd |= not_def & (1u << i);
+        no |= (not_def | not_e) & (1u << i);
+    }
+    d16 = ~nd & 0xffffu;
+    o16 = ~no & 0xffffu;
+}
+
 // Bits with D=1 are definite and take their value from O; bits with D=0 copy the nearest
 // definite bit below (:1675).  That is the carry into each bit of (O|~D) + O.  Bit 0 must be in D.
 MODES_SERIAL_FN void fill_copies(const uint32_t D[4], const uint32_t O[4], uint32_t F[4]) {
@@ -303,6 +380,7 @@ MODES_SERIAL_FN uint32_t magnitude_of(const uint16_t *lut_iq, uint32_t iq) {
 // Evaluate one candidate.  win: its kWindowWords staged words (modified); odd: see above;
 // at_buffer_start: j == 0, where the reference retries without correcting (dump1090.c:1660);
 // rec: the 12 words of pass[0] and pass[1] of its modes_candidate.
+template <bool kLean>
 MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start, int fix_errors, int aggressive,
                               const Tables &tab, uint32_t rec[12]) {
     const uint32_t shift = odd ? 32u : 16u;
@@ -310,7 +388,10 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
     uint32_t prev = 0, dsum = 0, d56 = 0;
     uint32_t wa = win[8];
 #pragma unroll 1
-    for (int k = 0; k < 7; k++) put16(F, k, first_pass_block(win, k, shift, tab.lut_iq, wa, prev, dsum, d56));
+    for (int k = 0; k < 7; k++) {
+        if constexpr (kLean) put16(F, k, first_pass_block_lean(win, k, shift, tab.lut_iq, wa, prev, dsum, d56));
+        else put16(F, k, first_pass_block(win, k, shift, tab.lut_iq, wa, prev, dsum, d56));
+    }
     const uint32_t d112 = dsum;
     uint32_t *pairs = win + 8;
     const uint32_t tri1 = (pairs[0] & 0xffffu) == (pairs[0] >> 16);
@@ -347,17 +428,35 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
             // forwards a previous 1 scales up, backwards a following 1 scales down; the first
             // bit handled always scales up
             const uint32_t f_one = fwd ? up : down, f_zero = fwd ? down : up;
-            uint32_t prev_e = fwd ? 1u : 0u;
-            const int step = fwd ? 1 : -1;
-            const uint32_t *cp = fwd ? pairs : pairs + 111;
             uint32_t Dm[4] = {0u, 0u, 0u, 0u}, Om[4] = {0u, 0u, 0u, 0u}, tri2 = 0;
-#pragma unroll 1
-            for (int k = 0; k < 7; k++, cp += 16 * step) {
-                uint32_t d16, o16;
-                correct_slice_block(cp, step, fwd, fwd && k == 0, !fwd && k == 6, f_one, f_zero, prev_e, d16, o16, tri2);
-                if (!fwd) { d16 = bitrev(d16) >> 16; o16 = bitrev(o16) >> 16; }      // walk order -> frame order
-                put16(Dm, fwd ? k : 6 - k, d16);
-                put16(Om, fwd ? k : 6 - k, o16);
+            if constexpr (kLean) {
+                const int step = fwd ? 1 : -1;
+                // forwards the first half-bit sample (low half of a pair) is rescaled, backwards the second
+                const uint32_t sel_x = fwd ? 0x4410u : 0x4432u, sel_y = fwd ? 0x4432u : 0x4410u;
+                const uint32_t dir = fwd ? 0u : ~0u;
+                const uint32_t g_one = opaque(f_one), g_pick = opaque(f_one ^ f_zero);
+                uint32_t not_e = fwd ? 0u : ~0u;               // the first bit handled always scales up
+                const uint32_t *cp = fwd ? pairs : pairs + 111;
+    #pragma unroll 1
+                for (int k = 0; k < 7; k++, cp += 16 * step) {
+                    uint32_t d16, o16;
+                    correct_slice_block_lean(cp, step, sel_x, sel_y, dir, fwd && k == 0, !fwd && k == 6, g_one, g_pick, not_e, d16, o16, tri2);
+                    if (!fwd) { d16 = bitrev(d16) >> 16; o16 = bitrev(o16) >> 16; }      // walk order -> frame order
+                    put16(Dm, fwd ? k : 6 - k, d16);
+                    put16(Om, fwd ? k : 6 - k, o16);
+                }
+            } else {
+                uint32_t prev_e = fwd ? 1u : 0u;
+                const int step = fwd ? 1 : -1;
+                const uint32_t *cp = fwd ? pairs : pairs + 111;
+    #pragma unroll 1
+                for (int k = 0; k < 7; k++, cp += 16 * step) {
+                    uint32_t d16, o16;
+                    correct_slice_block(cp, step, fwd, fwd && k == 0, !fwd && k == 6, f_one, f_zero, prev_e, d16, o16, tri2);
+                    if (!fwd) { d16 = bitrev(d16) >> 16; o16 = bitrev(o16) >> 16; }      // walk order -> frame order
+                    put16(Dm, fwd ? k : 6 - k, d16);
+                    put16(Om, fwd ? k : 6 - k, o16);
+                }
             }
             uint32_t G[4];
             fill_copies(Dm, Om, G);

@@ -849,6 +849,9 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_shared, const uint32_t *s
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 
+// kLean selects the leaner instruction sequences of modes_eval_serial.cuh for the two per-bit loops
+// (MODES_EVAL_VARIANT=lean; same results, checked on the host; not yet timed on a GPU).
+template <bool kLean>
 __global__ void __launch_bounds__(kSerThreads, 1)
 eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
                    uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive) {
@@ -918,7 +921,7 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
             const uint64_t t = (uint64_t)my_v - 2;
             const uint32_t odd = my_v > (uint32_t)kHaloSamples ? ((my_v - 1 - kHaloSamples) & 1u) : 0u;
             rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
-            serial::evaluate(wwin + lane * kSerRow, odd, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive,
+            serial::evaluate<kLean>(wwin + lane * kSerRow, odd, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive,
                              T, rec + 2);
         }
         __syncwarp();
@@ -934,30 +937,40 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
     }
 }
 
-// MODES_EVAL_VARIANT=warp selects the warp-per-candidate kernel (the first formulation; kept for
-// comparison and as a second implementation in the parity tests).
-static int eval_variant() {                       // read per launch (tests switch it within one process)
+// MODES_EVAL_VARIANT: "warp" selects the warp-per-candidate kernel (the first formulation; kept for
+// comparison and as a second implementation in the parity tests), "lean" the thread-per-candidate
+// kernel with the leaner per-bit loops.  Read per launch (tests switch it within one process).
+static int eval_variant() {
     const char *e = std::getenv("MODES_EVAL_VARIANT");
-    return (e && e[0] == 'w') ? 1 : 0;
+    if (!e) return 0;
+    return e[0] == 'w' ? 1 : (e[0] == 'l' ? 2 : 0);
+}
+
+template <bool kLean>
+static void launch_eval_serial(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
+                               int fix_errors, int aggressive, int sm_count, cudaStream_t stream) {
+    // the opt-in to > 48 KB of dynamic shared memory is per device
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaFuncSetAttribute(eval_serial_kernel<kLean>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes);
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    eval_serial_kernel<kLean><<<sm_count, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
+                                                                                   scan.cand_capacity, records, fix_errors, aggressive);
 }
 
 void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
                  modes_candidate *records, int fix_errors, int aggressive, int sm_count,
                  cudaStream_t stream) {
-    if (eval_variant() == 1) {
+    const int variant = eval_variant();
+    if (variant == 1)
         eval_kernel<<<sm_count * 4, kEvalThreads, 0, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
                                                               records, fix_errors, aggressive);
-        return;
-    }
-    // the opt-in to > 48 KB of dynamic shared memory is per device
-    static bool configured[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(eval_serial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSerSmemBytes);
-        if (dev >= 0 && dev < 64) configured[dev] = true;
-    }
-    eval_serial_kernel<<<sm_count, kSerThreads, kSerSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters,
-                                                                            scan.cand_capacity, records, fix_errors, aggressive);
+    else if (variant == 2)
+        launch_eval_serial<true>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    else
+        launch_eval_serial<false>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
 }
 
 // ------------------------------------------------------- magnitude (tests)

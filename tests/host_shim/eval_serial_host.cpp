@@ -16,7 +16,7 @@ bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out);
 
 // virt: the virtual sample array as bytes: 480 halo bytes (2 unused samples + 238 carried) then the body.
 extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samples, const uint32_t *cand_v, uint32_t n,
-                                    int fix_errors, int aggressive, modes_candidate *out) {
+                                    int fix_errors, int aggressive, int lean, modes_candidate *out) {
     using namespace modes::serial;
     static uint32_t bit_syn[112], fix_hash[256];
     static std::vector<uint32_t> nib_syn(28 * 16);
@@ -46,7 +46,8 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
         }
         const uint64_t t = (uint64_t)v - 2;
         uint32_t rec[12];
-        evaluate(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
+        if (lean) evaluate<true>(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
+        else evaluate<false>(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
         std::memset(&out[c], 0, sizeof(out[c]));
         out[c].t = (int64_t)t;
         std::memcpy(&out[c].pass[0], rec, 24);

@@ -21,7 +21,7 @@ def shim(checker_libs):
     lib = ctypes.CDLL(str(SHIM))
     lib.shim_eval_candidates.restype = ctypes.c_int
     lib.shim_eval_candidates.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32,
-                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     return lib
 
 
@@ -55,7 +55,7 @@ def _tie_rich(seed, n_frames=1500, levels=(0, 0, 1, 40, 100)):
 STREAMS = dict(_streams())
 
 
-def _evaluate(shim, data, fix, aggressive):
+def _evaluate(shim, data, fix, aggressive, lean):
     exp = C.oracle_scan_candidates(data, fix=fix, aggressive=aggressive, cap=400000)
     want = np.frombuffer(b"".join(bytes(c) for c in exp), dtype=api.CANDIDATE_DTYPE)
     nbuf = data.size // api.BUFFER_BYTES + 1
@@ -63,7 +63,7 @@ def _evaluate(shim, data, fix, aggressive):
     virt[480: 480 + data.size] = data
     v = (want["t"] + 2).astype(np.uint32)
     got = np.zeros(want.size, dtype=api.CANDIDATE_DTYPE)
-    rc = shim.shim_eval_candidates(virt.ctypes.data, virt.size // 2, v.ctypes.data, v.size, fix, aggressive,
+    rc = shim.shim_eval_candidates(virt.ctypes.data, virt.size // 2, v.ctypes.data, v.size, fix, aggressive, lean,
                                    got.ctypes.data)
     assert rc == 0
     return got.view(np.uint8).reshape(-1, 56), want.view(np.uint8).reshape(-1, 56)
@@ -71,8 +71,9 @@ def _evaluate(shim, data, fix, aggressive):
 
 @pytest.mark.parametrize("name", list(STREAMS))
 @pytest.mark.parametrize("fix,aggressive", [(1, 0), (1, 1), (0, 0)])
-def test_serial_evaluation_matches_oracle(name, fix, aggressive, shim):
-    got, want = _evaluate(shim, STREAMS[name], fix, aggressive)
+@pytest.mark.parametrize("lean", [0, 1], ids=["default", "lean"])
+def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
+    got, want = _evaluate(shim, STREAMS[name], fix, aggressive, lean)
     assert want.shape[0] > 200
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, f"{bad.size} of {want.shape[0]} records differ, first at {bad[0]}: {got[bad[0]].tolist()} != {want[bad[0]].tolist()}"

@@ -44,10 +44,11 @@ def test_decode_matches_oracle(name, kw, gpu_decoder_factory, checker_libs):
 
 @pytest.mark.parametrize("name", list(STREAMS))
 @pytest.mark.parametrize("aggressive", [0, 1])
-@pytest.mark.parametrize("variant", ["serial", "warp"])
+@pytest.mark.parametrize("variant", ["serial", "warp", "lean"])
 def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory, checker_libs, monkeypatch):
     """Scan + frame-evaluation kernels: candidate set and both evaluated passes, record for record.
-    Both frame-evaluation kernels (thread per candidate, the default; warp per candidate)."""
+    All frame-evaluation kernels (thread per candidate, the default; warp per candidate; thread per
+    candidate with the leaner per-bit loops)."""
     import torch
     monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
     data = STREAMS[name]
