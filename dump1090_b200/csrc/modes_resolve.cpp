@@ -313,7 +313,16 @@ static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
         in_array = out.capacity - out.count < n ? out.capacity - out.count : n;
         modes_message *base = out.array + out.count;
         const Delivery *d = deliveries.data();
-        BuildPool::get().run(in_array, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) materialise(d[i], base + i); });
+        BuildPool::get().run(in_array, [=](size_t b, size_t e) {
+            for (size_t i = b; i < e; i++) {
+                if (i + 6 < e) {                           // the records lie scattered (see judge_tiles): ask early
+                    const char *q = reinterpret_cast<const char *>(d[i + 6].eval);
+                    __builtin_prefetch(q, 0, 1);
+                    __builtin_prefetch(q + sizeof(modes_frame_eval) - 1, 0, 1);
+                }
+                materialise(d[i], base + i);
+            }
+        });
     }
     if (out.sink) {
         for (size_t i = 0; i < n; i++) {
