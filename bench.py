@@ -136,8 +136,9 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(1e3 * dt / args.steps, 3), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic: " + what,
-        "config": {"workload": "modes1.bin tiled to 1 GiB, --no-fix (BASELINE.json configs[1])",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic: " + what + " to 1 GiB per GPU",
+        # same workload definition as the GPU arm; what one timed step of THIS arm covers is in `sample`
+        "config": {"workload": "modes1.bin tiled to 1 GiB per GPU, --no-fix (BASELINE.json configs[1])",
                    "flags": "--no-fix", "samples_per_step": sample_bytes // 2},
         "cpu_baseline": {"value": round(value, 2), "unit": "Msamples/s", "cores": len(slices), "kind": kind,
                          "sample": sample},
