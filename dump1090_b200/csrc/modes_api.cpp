@@ -271,8 +271,12 @@ int run_buffers(modes_ctx *ctx, const uint8_t *host_iq, size_t n_buffers) {
     size_t max_b = (size_t)(ctx->cfg.max_batch_bytes / MODES_BUFFER_BYTES);
     if (max_b < 1) max_b = 1;
     int cur = 0;
+    constexpr size_t kTaperFloor = 16;                   // buffers (4 MiB)
     while (n_buffers) {
         size_t nb = n_buffers < max_b ? n_buffers : max_b;
+        // The last batches of a call halve in size: what remains to be done after the final upload
+        // (its kernels, record download and resolve) then belongs to a small batch, not a full one.
+        if (n_buffers <= max_b && n_buffers > kTaperFloor) nb = (n_buffers + 1) / 2;
         Slot &s = ctx->slot[cur];
         if (collect(ctx, s)) return -1;                                  // slot may still hold batch b-2
         s.buffer_base = ctx->buffers_done;
