@@ -110,7 +110,10 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
-           "modes_host_free", "modes_get_kernel_times", "modes_launch_count"]
+           "modes_host_free", "modes_get_kernel_times", "modes_launch_count",
+           "modes_tracker_create", "modes_tracker_destroy", "modes_tracker_update", "modes_tracker_count",
+           "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
+           "modes_format_sbs", "modes_cpr_nl"]
 
 
 def lib():
@@ -461,3 +464,94 @@ class Resolver:
             self.close()
         except Exception:
             pass
+
+
+# ---- aircraft tracker (host only) -------------------------------------
+
+class Aircraft(C.Structure):
+    """struct modes_aircraft == struct aircraft (dump1090.c:112-130)."""
+    _fields_ = [("addr", C.c_uint32), ("hexaddr", C.c_char * 7), ("flight", C.c_char * 9),
+                ("altitude", C.c_int32), ("speed", C.c_int32), ("track", C.c_int32),
+                ("seen", C.c_int64), ("messages", C.c_int64),
+                ("odd_cprlat", C.c_int32), ("odd_cprlon", C.c_int32), ("even_cprlat", C.c_int32), ("even_cprlon", C.c_int32),
+                ("lat", C.c_double), ("lon", C.c_double), ("odd_cprtime", C.c_int64), ("even_cprtime", C.c_int64)]
+
+    def as_tuple(self):
+        return (self.addr, self.hexaddr, self.flight, self.altitude, self.speed, self.track, self.seen, self.messages,
+                self.odd_cprlat, self.odd_cprlon, self.even_cprlat, self.even_cprlon, self.lat, self.lon,
+                self.odd_cprtime, self.even_cprtime)
+
+
+class Tracker:
+    """Per-aircraft state over a delivered message stream: the reference's interactiveReceiveData
+    with CPR position decoding, plus the SBS and JSON record formats.  Needs no GPU."""
+
+    def __init__(self, check_crc: int = 1):
+        L = lib()
+        L.modes_tracker_create.restype = C.c_void_p
+        L.modes_tracker_update.restype = C.POINTER(Aircraft)
+        L.modes_tracker_update.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.modes_tracker_count.restype = C.c_size_t
+        L.modes_tracker_count.argtypes = [C.c_void_p]
+        L.modes_tracker_list.restype = C.c_size_t
+        L.modes_tracker_list.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_tracker_expire.restype = C.c_size_t
+        L.modes_tracker_expire.argtypes = [C.c_void_p, C.c_int64, C.c_int]
+        L.modes_tracker_reference.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.modes_tracker_format_json.restype = C.c_size_t
+        L.modes_tracker_format_json.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+        L.modes_tracker_destroy.argtypes = [C.c_void_p]
+        L.modes_format_sbs.restype = C.c_size_t
+        L.modes_format_sbs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        self._h = L.modes_tracker_create(int(check_crc))
+        if not self._h:
+            raise MemoryError("modes_tracker_create failed")
+
+    def update(self, msg: "Message", now_ms: int):
+        """Returns (Aircraft copy, SBS line) or None when the message is ignored."""
+        p = lib().modes_tracker_update(self._h, C.byref(msg), int(now_ms))
+        if not p:
+            return None
+        buf = C.create_string_buffer(512)
+        n = lib().modes_format_sbs(C.byref(msg), p, buf, 512)
+        a = Aircraft()
+        C.memmove(C.byref(a), p, C.sizeof(Aircraft))
+        return a, buf.raw[:n].decode("latin1")
+
+    def aircraft(self):
+        n = lib().modes_tracker_count(self._h)
+        arr = (Aircraft * max(n, 1))()
+        lib().modes_tracker_list(self._h, arr, n)
+        return [arr[i] for i in range(n)]
+
+    def expire(self, now_ms: int, ttl_seconds: int) -> int:
+        return int(lib().modes_tracker_expire(self._h, int(now_ms), int(ttl_seconds)))
+
+    def reference(self):
+        lat, lon, cnt = C.c_double(), C.c_double(), C.c_int()
+        lib().modes_tracker_reference(self._h, C.byref(lat), C.byref(lon), C.byref(cnt))
+        return lat.value, lon.value, cnt.value
+
+    def json(self, metric: int = 0) -> str:
+        need = lib().modes_tracker_format_json(self._h, int(metric), None, 0)
+        buf = C.create_string_buffer(need + 1)
+        lib().modes_tracker_format_json(self._h, int(metric), buf, need + 1)
+        return buf.raw[:need].decode("latin1")
+
+    def close(self):
+        if self._h:
+            lib().modes_tracker_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cpr_nl(lat: float) -> int:
+    f = lib().modes_cpr_nl
+    f.restype = C.c_int
+    f.argtypes = [C.c_double]
+    return int(f(float(lat)))

@@ -6,7 +6,10 @@
  * Supported options (same spelling and meaning as the reference):
  *   --ifile <file>  --raw  --onlyaddr  --no-fix  --no-crc-check  --aggressive  --stats
  * Additions: --drop-eof-buffer (reproduce the stock binary's usual EOF race
- * outcome), --device <n>, --chunk <bytes> (read size).
+ * outcome), --device <n>, --chunk <bytes> (read size); --sbs prints the SBS (BaseStation)
+ * line of every message instead (what the reference writes to port 30003, dump1090.c:2396) and
+ * --aircraft-json prints the tracked aircraft as the reference's /data.json at the end (:2505),
+ * both with stream time (sample position / 2 MHz) as the clock.
  * The live-radio, networking and interactive options are out of scope.
  */
 #include <stdio.h>
@@ -14,13 +17,23 @@
 #include <string.h>
 #include "modes_b200.h"
 
-static int opt_raw = 0, opt_onlyaddr = 0, opt_stats = 0, opt_check_crc = 1;
+static int opt_raw = 0, opt_onlyaddr = 0, opt_stats = 0, opt_check_crc = 1, opt_sbs = 0, opt_json = 0;
+static modes_tracker *tracker = NULL;
 
 /* Message sink: the --raw / --onlyaddr forms of displayModesMessage
  * (dump1090.c:1318-1331) and, by default, the full text (:1314-1450) via modes_format_message(). */
 static void on_message(void *user, const modes_message *mm) {
     (void)user;
     if (opt_stats) return;                                  /* dump1090.c:1803 */
+    if (tracker) {                                          /* dump1090.c:1806-1809 */
+        const modes_aircraft *a = modes_tracker_update(tracker, mm, mm->sample_pos / 2000);
+        if (a && opt_sbs) {
+            char line[512];
+            size_t n = modes_format_sbs(mm, a, line, sizeof(line));
+            fwrite(line, 1, n < sizeof(line) ? n : sizeof(line) - 1, stdout);
+        }
+        if (opt_sbs || opt_json) return;
+    }
     if (opt_onlyaddr) {
         printf("%02x%02x%02x\n", mm->aa1, mm->aa2, mm->aa3);
         return;
@@ -52,6 +65,8 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[j], "--aggressive")) cfg.aggressive = 1;
         else if (!strcmp(argv[j], "--stats")) opt_stats = 1;
         else if (!strcmp(argv[j], "--drop-eof-buffer")) cfg.drop_eof_buffer = 1;
+        else if (!strcmp(argv[j], "--sbs")) opt_sbs = 1;
+        else if (!strcmp(argv[j], "--aircraft-json")) opt_json = 1;
         else if (!strcmp(argv[j], "--device") && more) cfg.device = atoi(argv[++j]);
         else if (!strcmp(argv[j], "--chunk") && more) chunk = (size_t)strtoull(argv[++j], NULL, 10);
         else {
@@ -65,6 +80,10 @@ int main(int argc, char **argv) {
 
     modes_ctx *ctx = modes_create(&cfg);
     if (!ctx) { fprintf(stderr, "modes_create: %s\n", modes_last_error(NULL)); return 1; }
+    if (opt_sbs || opt_json) {
+        tracker = modes_tracker_create(cfg.check_crc);
+        if (!tracker) { fprintf(stderr, "out of memory\n"); return 1; }
+    }
     modes_set_sink(ctx, on_message, NULL);
     unsigned char *buf = (unsigned char *)modes_host_alloc(chunk);
     if (!buf) { fprintf(stderr, "out of memory\n"); return 1; }
@@ -86,6 +105,12 @@ int main(int argc, char **argv) {
         printf("%lld two bits errors\n", (long long)st.v[7]);
         printf("%lld total usable messages\n", (long long)(st.v[3] + st.v[5]));
     }
+    if (opt_json) {
+        size_t need = modes_tracker_format_json(tracker, 0, NULL, 0);
+        char *json = (char *)malloc(need + 1);
+        if (json) { modes_tracker_format_json(tracker, 0, json, need + 1); fwrite(json, 1, need, stdout); free(json); }
+    }
+    modes_tracker_destroy(tracker);
     modes_host_free(buf);
     modes_destroy(ctx);
     if (f != stdin) fclose(f);

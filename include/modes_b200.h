@@ -215,6 +215,50 @@ size_t modes_format_raw_net(const modes_message *mm, char *buf, size_t capacity)
  * discards the line.  Feed the bytes to modes_decode_frame() for the decoding half. */
 int    modes_parse_hex_line(const char *line, uint8_t msg[14]);
 
+/* ---- SURVEY.md §8(f) item 3 — aircraft tracker, CPR positions, SBS / JSON records -------------
+ * The per-aircraft reduce over the delivered message stream that the reference's interactive
+ * mode, HTTP map and SBS port share (dump1090.c:1822-2164).  Pure host code, no GPU involved.
+ * Time is supplied by the caller in milliseconds: wall clock for a live feed (what the reference
+ * uses, time()/mstime()), or stream time (modes_message.sample_pos / 2000) for a file. */
+typedef struct modes_tracker modes_tracker;
+
+/* struct aircraft (dump1090.c:112-130) */
+typedef struct modes_aircraft {
+    uint32_t addr;                  /* ICAO address */
+    char     hexaddr[7];            /* "%06x" */
+    char     flight[9];
+    int32_t  altitude, speed, track;
+    int64_t  seen;                  /* seconds: now_ms / 1000 at the last message (time(NULL) in the reference) */
+    int64_t  messages;
+    int32_t  odd_cprlat, odd_cprlon, even_cprlat, even_cprlon;
+    double   lat, lon;
+    int64_t  odd_cprtime, even_cprtime;   /* ms (mstime() in the reference) */
+} modes_aircraft;
+
+/* check_crc: messages with crcok == 0 are ignored when set (dump1090.c:2073). */
+modes_tracker *modes_tracker_create(int check_crc);
+void   modes_tracker_destroy(modes_tracker *t);
+/* interactiveReceiveData() (dump1090.c:2069-2164) incl. decodeCPR (:1952-1988), decodeCPRSurface
+ * (:2004-2052), decodeMovementField (:2056-2066) and the receiver reference position.  Returns
+ * the aircraft (valid until the next expire/destroy) or NULL when the message is ignored. */
+const modes_aircraft *modes_tracker_update(modes_tracker *t, const modes_message *mm, int64_t now_ms);
+size_t modes_tracker_count(const modes_tracker *t);
+/* The aircraft in the reference's list order: most recently created first (dump1090.c:2080-2083). */
+size_t modes_tracker_list(const modes_tracker *t, modes_aircraft *out, size_t capacity);
+/* interactiveRemoveStaleAircrafts() (dump1090.c:2205-2229): drops aircraft not heard for more than
+ * ttl_seconds; returns how many were removed. */
+size_t modes_tracker_expire(modes_tracker *t, int64_t now_ms, int ttl_seconds);
+/* Receiver reference position (running mean of decoded airborne positions, dump1090.c:2127-2141). */
+void   modes_tracker_reference(const modes_tracker *t, double *lat, double *lon, int *count);
+/* aircraftsToJson() (dump1090.c:2505-2551).  Returns the length needed; writes at most capacity-1 bytes + NUL. */
+size_t modes_tracker_format_json(const modes_tracker *t, int metric, char *buf, size_t capacity);
+/* One SBS (BaseStation, port 30003) line for a message and its aircraft, modesSendSBSOutput()
+ * (dump1090.c:2396-2446), newline included.  Returns the length needed, 0 for message types that
+ * produce no line. */
+size_t modes_format_sbs(const modes_message *mm, const modes_aircraft *a, char *buf, size_t capacity);
+/* cprNLFunction (dump1090.c:1869-1931), exposed for tests. */
+int    modes_cpr_nl(double lat);
+
 /* ---- plumbing ----------------------------------------------------------- */
 void *modes_stream(modes_ctx *ctx);                    /* the cudaStream_t modes_detect_device launches on */
 int   modes_set_stream(modes_ctx *ctx, void *cuda_stream);   /* use the caller's stream for it (NULL: own) */

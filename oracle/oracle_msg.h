@@ -29,4 +29,18 @@ struct oracle_msg {
     int32_t  pad2;
     int64_t  sample_pos;        /* extra: stream sample index of the preamble start, -1 if unknown */
 };
+
+/* struct aircraft (dump1090.c:112-130) as the tracker tests read it back; same layout as
+ * modes_aircraft in include/modes_b200.h. */
+struct oracle_aircraft {
+    uint32_t addr;
+    char     hexaddr[7];
+    char     flight[9];
+    int32_t  altitude, speed, track;
+    int64_t  seen;
+    int64_t  messages;
+    int32_t  odd_cprlat, odd_cprlon, even_cprlat, even_cprlon;
+    double   lat, lon;
+    int64_t  odd_cprtime, even_cprtime;
+};
 #endif

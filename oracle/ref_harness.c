@@ -34,9 +34,20 @@ time_t ref_frozen_time(time_t *t);
 
 #include "oracle_msg.h"
 
+/* The clock the reference sees: frozen at 10^9 s for the decode tests, set per message by the
+ * tracker door below (time() and gettimeofday() are both redirected by the build recipe). */
+#define REF_CLOCK_DEFAULT_MS 1000000000000LL
+static long long g_clock_ms = REF_CLOCK_DEFAULT_MS;
 time_t ref_frozen_time(time_t *t) {
-    if (t) *t = 1000000000;
-    return 1000000000;
+    time_t v = (time_t)(g_clock_ms / 1000);
+    if (t) *t = v;
+    return v;
+}
+int ref_gettimeofday(struct timeval *tv, void *tz) {
+    (void)tz;
+    tv->tv_sec = g_clock_ms / 1000;
+    tv->tv_usec = (g_clock_ms % 1000) * 1000;
+    return 0;
 }
 
 static struct oracle_msg *g_out = NULL;
@@ -92,6 +103,7 @@ static void ref_reset(int fix_errors, int aggressive, int check_crc, int stats) 
     Modes.stats = stats;
     Modes.interactive = 0;
     Modes.net = 0;
+    g_clock_ms = REF_CLOCK_DEFAULT_MS;
     memset(Modes.data, 127, Modes.data_len);                                   /* :344 */
     memset(Modes.icao_cache, 0, sizeof(uint32_t) * MODES_ICAO_CACHE_LEN * 2);  /* :336 */
     Modes.stat_valid_preamble = 0; Modes.stat_demodulated = 0;
@@ -188,6 +200,104 @@ void ref_time_phases(const unsigned char *iq, size_t nbytes, int fix_errors, int
         }
     }
 }
+
+/* ---- tracker door: the reference's interactiveReceiveData / decodeCPR /
+ * modesSendSBSOutput / aircraftsToJson driven message by message with an explicit clock. */
+static char g_sbs[512];
+static int g_sbs_len = 0;
+void ref_harness_net_sink(int service, void *msg, int len) {
+    (void)service;
+    if (len > (int)sizeof(g_sbs) - 1) len = (int)sizeof(g_sbs) - 1;
+    memcpy(g_sbs, msg, len);
+    g_sbs_len = len;
+}
+
+static void copy_aircraft(struct oracle_aircraft *o, const struct aircraft *a) {
+    memset(o, 0, sizeof(*o));
+    o->addr = a->addr;
+    memcpy(o->hexaddr, a->hexaddr, 7);
+    memcpy(o->flight, a->flight, 9);
+    o->altitude = a->altitude; o->speed = a->speed; o->track = a->track;
+    o->seen = a->seen; o->messages = a->messages;
+    o->odd_cprlat = a->odd_cprlat; o->odd_cprlon = a->odd_cprlon;
+    o->even_cprlat = a->even_cprlat; o->even_cprlon = a->even_cprlon;
+    o->lat = a->lat; o->lon = a->lon;
+    o->odd_cprtime = a->odd_cprtime; o->even_cprtime = a->even_cprtime;
+}
+
+void ref_track_reset(int check_crc) {
+    ref_reset(1, 0, check_crc, 0);
+    while (Modes.aircrafts) { struct aircraft *n = Modes.aircrafts->next; free(Modes.aircrafts); Modes.aircrafts = n; }
+    Modes.ref_lat = Modes.ref_lon = 0;
+    Modes.ref_count = 0;
+    Modes.sbsos = 7;                    /* any value: the fan-out is intercepted */
+}
+
+/* Returns 1 and fills *out (and sbs: the SBS line, "" when the message type has none) when the
+ * reference tracked the message, 0 when it ignored it. */
+int ref_track_update(const struct oracle_msg *m, long long now_ms, struct oracle_aircraft *out, char *sbs512) {
+    struct modesMessage mm;
+    memset(&mm, 0, sizeof(mm));
+    memcpy(mm.msg, m->msg, 14);
+    mm.msgbits = m->msgbits; mm.msgtype = m->msgtype; mm.crcok = m->crcok; mm.crc = m->crc;
+    mm.errorbit = m->errorbit; mm.aa1 = m->aa1; mm.aa2 = m->aa2; mm.aa3 = m->aa3;
+    mm.phase_corrected = m->phase_corrected; mm.ca = m->ca; mm.iid = m->iid;
+    mm.metype = m->metype; mm.mesub = m->mesub; mm.heading_is_valid = m->heading_is_valid;
+    mm.heading = m->heading; mm.aircraft_type = m->aircraft_type; mm.fflag = m->fflag; mm.tflag = m->tflag;
+    mm.raw_latitude = m->raw_latitude; mm.raw_longitude = m->raw_longitude;
+    memcpy(mm.flight, m->flight, 9);
+    mm.ew_dir = m->ew_dir; mm.ew_velocity = m->ew_velocity; mm.ns_dir = m->ns_dir; mm.ns_velocity = m->ns_velocity;
+    mm.vert_rate_source = m->vert_rate_source; mm.vert_rate_sign = m->vert_rate_sign;
+    mm.vert_rate = m->vert_rate; mm.velocity = m->velocity;
+    mm.movement = m->movement; mm.movement_valid = m->movement_valid;
+    mm.ground_track = m->ground_track; mm.ground_track_valid = m->ground_track_valid;
+    mm.fs = m->fs; mm.dr = m->dr; mm.um = m->um; mm.identity = m->identity;
+    mm.altitude = m->altitude; mm.unit = m->unit;
+    g_clock_ms = now_ms;
+    struct aircraft *a = interactiveReceiveData(&mm);
+    if (sbs512) sbs512[0] = 0;
+    if (!a) return 0;
+    g_sbs_len = 0;
+    modesSendSBSOutput(&mm, a);
+    if (sbs512) { memcpy(sbs512, g_sbs, g_sbs_len); sbs512[g_sbs_len] = 0; }
+    copy_aircraft(out, a);
+    return 1;
+}
+
+long ref_track_list(struct oracle_aircraft *out, long cap) {
+    long n = 0;
+    for (struct aircraft *a = Modes.aircrafts; a; a = a->next, n++)
+        if (n < cap) copy_aircraft(out + n, a);
+    return n;
+}
+
+long ref_track_expire(long long now_ms, int ttl_seconds) {
+    long before = 0, after = 0;
+    for (struct aircraft *a = Modes.aircrafts; a; a = a->next) before++;
+    g_clock_ms = now_ms;
+    Modes.interactive_ttl = ttl_seconds;
+    interactiveRemoveStaleAircrafts();
+    for (struct aircraft *a = Modes.aircrafts; a; a = a->next) after++;
+    return before - after;
+}
+
+int ref_track_json(int metric, char *buf, int cap) {
+    int len = 0;
+    Modes.metric = metric;
+    char *c = aircraftsToJson(&len);
+    Modes.metric = 0;
+    int n = len < cap - 1 ? len : cap - 1;
+    memcpy(buf, c, n);
+    buf[n] = 0;
+    free(c);
+    return len;
+}
+
+void ref_track_reference(double *lat, double *lon, int *count) {
+    *lat = Modes.ref_lat; *lon = Modes.ref_lon; *count = Modes.ref_count;
+}
+
+int ref_cpr_nl(double lat) { return cprNLFunction(lat); }
 
 /* ctypes entry: the two reference kernels on one caller-supplied buffer image
  * (262620 bytes, carry included) — lets tests pin the magnitude vector. */

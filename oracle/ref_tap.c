@@ -5,3 +5,8 @@
  * struct layout. */
 void ref_harness_sink(void *mm);
 void useModesMessage(void *mm) { ref_harness_sink(mm); }
+
+/* Same trick for the network fan-out (dump1090.c:2346): the harness captures what
+ * modesSendSBSOutput() would have written to its clients. */
+void ref_harness_net_sink(int service, void *msg, int len);
+void modesSendAllClients(int service, void *msg, int len) { ref_harness_net_sink(service, msg, len); }

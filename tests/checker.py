@@ -211,3 +211,66 @@ def modes1_path() -> Path:
 
 def modes1() -> np.ndarray:
     return np.fromfile(modes1_path(), dtype=np.uint8)
+
+
+# ---- tracker door of the reference harness -----------------------------
+
+class Aircraft(ctypes.Structure):
+    """struct oracle_aircraft (oracle/oracle_msg.h) == struct aircraft, dump1090.c:112-130."""
+    _fields_ = [("addr", ctypes.c_uint32), ("hexaddr", ctypes.c_char * 7), ("flight", ctypes.c_char * 9),
+                ("altitude", ctypes.c_int32), ("speed", ctypes.c_int32), ("track", ctypes.c_int32),
+                ("seen", ctypes.c_int64), ("messages", ctypes.c_int64),
+                ("odd_cprlat", ctypes.c_int32), ("odd_cprlon", ctypes.c_int32),
+                ("even_cprlat", ctypes.c_int32), ("even_cprlon", ctypes.c_int32),
+                ("lat", ctypes.c_double), ("lon", ctypes.c_double),
+                ("odd_cprtime", ctypes.c_int64), ("even_cprtime", ctypes.c_int64)]
+
+    def as_tuple(self):
+        return (self.addr, self.hexaddr, self.flight, self.altitude, self.speed, self.track, self.seen, self.messages,
+                self.odd_cprlat, self.odd_cprlon, self.even_cprlat, self.even_cprlon, self.lat, self.lon,
+                self.odd_cprtime, self.even_cprtime)
+
+
+class RefTracker:
+    """The reference's own interactiveReceiveData / modesSendSBSOutput / aircraftsToJson, one
+    message at a time with an explicit clock."""
+
+    def __init__(self, check_crc=1):
+        self.lib = ref_lib()
+        self.lib.ref_track_reset(int(check_crc))
+        self.lib.ref_track_list.restype = ctypes.c_long
+        self.lib.ref_track_expire.restype = ctypes.c_long
+
+    def update(self, msg, now_ms):
+        """msg: any ctypes struct with the oracle_msg layout (Msg here, api.Message)."""
+        m = Msg()
+        ctypes.memmove(ctypes.byref(m), ctypes.byref(msg), ctypes.sizeof(Msg))
+        a = Aircraft()
+        sbs = ctypes.create_string_buffer(512)
+        ok = self.lib.ref_track_update(ctypes.byref(m), ctypes.c_longlong(int(now_ms)), ctypes.byref(a), sbs)
+        return (a, sbs.value.decode("latin1")) if ok else None
+
+    def aircraft(self):
+        arr = (Aircraft * 4096)()
+        n = self.lib.ref_track_list(arr, 4096)
+        return [arr[i] for i in range(n)]
+
+    def expire(self, now_ms, ttl_seconds):
+        return int(self.lib.ref_track_expire(ctypes.c_longlong(int(now_ms)), int(ttl_seconds)))
+
+    def reference(self):
+        lat, lon, cnt = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        self.lib.ref_track_reference(ctypes.byref(lat), ctypes.byref(lon), ctypes.byref(cnt))
+        return lat.value, lon.value, cnt.value
+
+    def json(self, metric=0):
+        buf = ctypes.create_string_buffer(1 << 20)
+        n = self.lib.ref_track_json(int(metric), buf, 1 << 20)
+        return buf.raw[:n].decode("latin1")
+
+
+def ref_cpr_nl(lat):
+    f = ref_lib().ref_cpr_nl
+    f.restype = ctypes.c_int
+    f.argtypes = [ctypes.c_double]
+    return int(f(float(lat)))

@@ -13,9 +13,9 @@ FLAG_SETS = [dict(), dict(aggressive=1), dict(fix=0), dict(check_crc=0), dict(ch
 
 # "lean" (thread per candidate with the leaner per-bit loops) was written after the round's GPU
 # budget was spent: it is checked on the host (test_eval_serial_host.py) and joins this matrix with
-# MODES_TEST_LEAN=1 until it has been run on hardware once.
+# MODES_TEST_UNVERIFIED=1 until it has been run on hardware once.
 import os
-EVAL_VARIANTS = ["serial", "warp"] + (["lean"] if os.environ.get("MODES_TEST_LEAN") else [])
+EVAL_VARIANTS = ["serial", "warp"] + (["lean"] if os.environ.get("MODES_TEST_UNVERIFIED") else [])
 
 
 def _dec_kw(kw):
