@@ -22,6 +22,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 #include "modes_b200.h"
 
@@ -157,13 +158,13 @@ struct Out {
 
 struct modes_tracker {
     int check_crc = 1;
-    std::deque<std::unique_ptr<modes_aircraft>> list;    // front = most recently created
+    std::deque<std::unique_ptr<modes_aircraft>> list;    // front = most recently created (the reference's list order)
+    std::unordered_map<uint32_t, modes_aircraft *> by_addr;   // the reference walks its list; an index keeps busy skies O(1)
     double ref_lat = 0, ref_lon = 0;
     int ref_count = 0;
     modes_aircraft *find(uint32_t addr) {
-        for (auto &a : list)
-            if (a->addr == addr) return a.get();
-        return nullptr;
+        auto it = by_addr.find(addr);
+        return it == by_addr.end() ? nullptr : it->second;
     }
 };
 
@@ -191,6 +192,7 @@ const modes_aircraft *modes_tracker_update(modes_tracker *t, const modes_message
         fresh->addr = addr;
         std::snprintf(fresh->hexaddr, sizeof(fresh->hexaddr), "%06x", (int)addr);
         a = fresh.get();
+        t->by_addr[addr] = a;
         t->list.push_front(std::move(fresh));
     }
     a->seen = now_ms / 1000;
@@ -258,7 +260,7 @@ size_t modes_tracker_expire(modes_tracker *t, int64_t now_ms, int ttl_seconds) {
     const int64_t now = now_ms / 1000;
     size_t removed = 0;
     for (auto it = t->list.begin(); it != t->list.end();) {
-        if ((now - (*it)->seen) > ttl_seconds) { it = t->list.erase(it); removed++; }
+        if ((now - (*it)->seen) > ttl_seconds) { t->by_addr.erase((*it)->addr); it = t->list.erase(it); removed++; }
         else ++it;
     }
     return removed;
