@@ -77,3 +77,25 @@ def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
     assert want.shape[0] > 200
     bad = np.nonzero((got != want).any(axis=1))[0]
     assert bad.size == 0, f"{bad.size} of {want.shape[0]} records differ, first at {bad[0]}: {got[bad[0]].tolist()} != {want[bad[0]].tolist()}"
+
+
+@pytest.mark.parametrize("lean", [0, 1], ids=["default", "lean"])
+def test_serial_evaluation_random_alphabets(lean, shim):
+    """Many small streams with random amplitude alphabets, preamble jitter and noise levels: weak
+    and saturated pairs, long indefinite runs, every gate outcome."""
+    rng = np.random.default_rng(2024)
+    total = 0
+    for case in range(24):
+        levels = tuple(int(x) for x in rng.choice([0, 0, 1, 2, 3, 5, 8, 20, 40, 70, 100, 127, 128], size=int(rng.integers(2, 6))))
+        data = _tie_rich(int(rng.integers(1, 1 << 30)), n_frames=int(rng.integers(60, 200)), levels=levels).copy()
+        if case % 3 == 0:                                                 # additive noise on top
+            noise = rng.integers(-3, 4, size=data.size)
+            data = np.clip(data.astype(np.int64) + noise, 0, 255).astype(np.uint8)
+        if case % 4 == 1:                                                 # saturated samples
+            data[rng.integers(0, data.size, size=data.size // 50)] = 255
+        for fix, aggressive in ((1, 1), (0, 0)):
+            got, want = _evaluate(shim, data, fix, aggressive, lean)
+            total += want.shape[0]
+            bad = np.nonzero((got != want).any(axis=1))[0]
+            assert bad.size == 0, f"case {case} levels {levels}: {bad.size} of {want.shape[0]} records differ"
+    assert total > 5000
