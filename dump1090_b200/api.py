@@ -113,7 +113,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count",
            "modes_tracker_create", "modes_tracker_destroy", "modes_tracker_update", "modes_tracker_count",
            "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
-           "modes_format_sbs", "modes_cpr_nl"]
+           "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl"]
 
 
 def lib():
@@ -536,6 +536,16 @@ class Tracker:
         need = lib().modes_tracker_format_json(self._h, int(metric), None, 0)
         buf = C.create_string_buffer(need + 1)
         lib().modes_tracker_format_json(self._h, int(metric), buf, need + 1)
+        return buf.raw[:need].decode("latin1")
+
+    def table(self, now_ms: int, metric: int = 0, max_rows: int = 15) -> str:
+        """The interactive-mode screen, dump1090.c:2167-2199."""
+        f = lib().modes_tracker_format_table
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_size_t]
+        need = f(self._h, int(metric), int(max_rows), int(now_ms), None, 0)
+        buf = C.create_string_buffer(need + 1)
+        f(self._h, int(metric), int(max_rows), int(now_ms), buf, need + 1)
         return buf.raw[:need].decode("latin1")
 
     def close(self):

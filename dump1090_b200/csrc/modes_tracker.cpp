@@ -9,6 +9,7 @@
 //   modes_cpr_nl            cprNLFunction                 :1869-1931
 //   modes_tracker_expire    interactiveRemoveStaleAircrafts :2205-2229
 //   modes_tracker_format_json  aircraftsToJson            :2505-2551
+//   modes_tracker_format_table interactiveShowData        :2167-2199
 //   modes_format_sbs        modesSendSBSOutput            :2396-2446
 //
 // The arithmetic is kept expression for expression (doubles, the int truncations, the order of
@@ -290,6 +291,28 @@ size_t modes_tracker_format_json(const modes_tracker *t, int metric, char *buf, 
     }
     if (any) o.add("\n");
     o.add("]\n");
+    return o.finish();
+}
+
+size_t modes_tracker_format_table(const modes_tracker *t, int metric, int max_rows, int64_t now_ms, char *buf, size_t capacity) {
+    Out o(buf, capacity);
+    const int64_t now = now_ms / 1000;
+    char progress[4] = {' ', ' ', ' ', 0};
+    progress[now % 3] = '.';
+    o.add("\x1b[H\x1b[2J");
+    o.add("Hex    Flight   Altitude  Speed   Lat       Lon       Track  Messages Seen %s\n"
+          "--------------------------------------------------------------------------------\n", progress);
+    int rows = 0;
+    if (t) {
+        for (const auto &a : t->list) {
+            if (rows >= max_rows) break;
+            int altitude = a->altitude, speed = a->speed;
+            if (metric) { altitude = (int)(altitude / 3.2828); speed = (int)(speed * 1.852); }
+            o.add("%-6s %-8s %-9d %-7d %-7.03f   %-7.03f   %-3d   %-9ld %d sec\n", a->hexaddr, a->flight, altitude, speed,
+                  a->lat, a->lon, a->track, (long)a->messages, (int)(now - a->seen));
+            rows++;
+        }
+    }
     return o.finish();
 }
 

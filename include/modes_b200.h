@@ -252,6 +252,9 @@ size_t modes_tracker_expire(modes_tracker *t, int64_t now_ms, int ttl_seconds);
 void   modes_tracker_reference(const modes_tracker *t, double *lat, double *lon, int *count);
 /* aircraftsToJson() (dump1090.c:2505-2551).  Returns the length needed; writes at most capacity-1 bytes + NUL. */
 size_t modes_tracker_format_json(const modes_tracker *t, int metric, char *buf, size_t capacity);
+/* The interactive-mode screen, interactiveShowData() (dump1090.c:2167-2199): clear-screen sequence,
+ * header with the activity dot, one row per aircraft up to max_rows.  Same length convention. */
+size_t modes_tracker_format_table(const modes_tracker *t, int metric, int max_rows, int64_t now_ms, char *buf, size_t capacity);
 /* One SBS (BaseStation, port 30003) line for a message and its aircraft, modesSendSBSOutput()
  * (dump1090.c:2396-2446), newline included.  Returns the length needed, 0 for message types that
  * produce no line. */

@@ -293,6 +293,32 @@ int ref_track_json(int metric, char *buf, int cap) {
     return len;
 }
 
+/* interactiveShowData() prints to stdout: borrow fd 1 for the call and read the text back. */
+int ref_track_table(int metric, int max_rows, long long now_ms, char *buf, int cap) {
+    char path[] = "/tmp/ref_table_XXXXXX";
+    int fd = mkstemp(path);
+    if (fd < 0) return -1;
+    fflush(stdout);
+    int saved = dup(1);
+    dup2(fd, 1);
+    g_clock_ms = now_ms;
+    Modes.metric = metric;
+    Modes.interactive_rows = max_rows;
+    interactiveShowData();
+    fflush(stdout);
+    dup2(saved, 1);
+    close(saved);
+    Modes.metric = 0;
+    off_t len = lseek(fd, 0, SEEK_END);
+    lseek(fd, 0, SEEK_SET);
+    int n = (int)(len < cap - 1 ? len : cap - 1);
+    if (read(fd, buf, n) != n) n = 0;
+    buf[n] = 0;
+    close(fd);
+    unlink(path);
+    return (int)len;
+}
+
 void ref_track_reference(double *lat, double *lon, int *count) {
     *lat = Modes.ref_lat; *lon = Modes.ref_lon; *count = Modes.ref_count;
 }

@@ -269,6 +269,12 @@ class RefTracker:
         return buf.raw[:n].decode("latin1")
 
 
+def ref_track_table(now_ms, metric=0, max_rows=15):
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = ref_lib().ref_track_table(int(metric), int(max_rows), ctypes.c_longlong(int(now_ms)), buf, 1 << 16)
+    return buf.raw[:n].decode("latin1")
+
+
 def ref_cpr_nl(lat):
     f = ref_lib().ref_cpr_nl
     f.restype = ctypes.c_int

@@ -43,6 +43,9 @@ def _run_both(messages, times, check_crc=1):
     assert got.reference() == ref.reference()
     for metric in (0, 1):
         assert got.json(metric) == ref.json(metric)
+        for rows in (3, 15, 100):
+            now = times[-1] + 4321 * (rows + metric)
+            assert got.table(now, metric, rows) == C.ref_track_table(now, metric, rows)
     return ref, got, tracked
 
 
