@@ -57,6 +57,9 @@ inline uint32_t tiles_for(uint64_t n_samples) {
 // Kernel launchers (modes_kernels.cu).  All asynchronous on `stream`.
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream);
+// K1 as rewritten in round 2 (modes_scan2.cu): lane = 32 consecutive positions, FMA/ALU-balanced compares.
+void launch_scan2(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
+                  cudaStream_t stream);
 void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
                  modes_candidate *records, int fix_errors, int aggressive, int sm_count,
                  cudaStream_t stream);

@@ -413,8 +413,11 @@ static void launch_scan_variant(const BatchView &in, const DeviceTables &tab, co
 
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream) {
-    static const int variant = [] { const char *e = getenv("MODES_SCAN_VARIANT"); return e ? atoi(e) : 1; }();
-    if (variant == 0) launch_scan_variant<0>(in, tab, out, sm_count, stream);
+    // read per launch: the tests switch variants within one process
+    const char *e = getenv("MODES_SCAN_VARIANT");
+    const int variant = e ? atoi(e) : 1;
+    if (variant == 2) launch_scan2(in, tab, out, sm_count, stream);
+    else if (variant == 0) launch_scan_variant<0>(in, tab, out, sm_count, stream);
     else launch_scan_variant<1>(in, tab, out, sm_count, stream);
 }
 

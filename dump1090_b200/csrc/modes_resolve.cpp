@@ -204,8 +204,13 @@ static inline void materialise(const Delivery &d, modes_message *mm) {
 class BuildPool {
   public:
     static BuildPool &get() { static BuildPool *p = new BuildPool();  /* never destroyed: workers are detached */ return *p; }
+    // One job at a time: the job state below (fn_, n_, next_, pending_) belongs to whoever holds
+    // job_mu_ for the whole job.  A second context on another thread that finds the pool busy
+    // builds its structs itself instead of waiting (distinct contexts are independent).
     void run(size_t n, const std::function<void(size_t, size_t)> &fn) {
         if (workers_.empty() || n < 2048) { fn(0, n); return; }
+        std::unique_lock<std::mutex> job(job_mu_, std::try_to_lock);
+        if (!job.owns_lock()) { fn(0, n); return; }
         std::unique_lock<std::mutex> lk(mu_);
         fn_ = &fn; n_ = n; next_ = 0; pending_ = workers_.size(); gen_++;
         cv_.notify_all();
@@ -244,6 +249,7 @@ class BuildPool {
         }
     }
     std::vector<std::thread> workers_;
+    std::mutex job_mu_;
     std::mutex mu_;
     std::condition_variable cv_, done_;
     const std::function<void(size_t, size_t)> *fn_ = nullptr;

@@ -9,7 +9,7 @@
  * outcome), --device <n>, --chunk <bytes> (read size); --sbs prints the SBS (BaseStation)
  * line of every message instead (what the reference writes to port 30003, dump1090.c:2396) and
  * --aircraft-json prints the tracked aircraft as the reference's /data.json at the end (:2505),
- * both with stream time (sample position / 2 MHz) as the clock.
+ * both with stream time (MODES_STREAM_EPOCH_MS + sample position / 2 MHz) as the clock.
  * The live-radio, networking and interactive options are out of scope.
  */
 #include <stdio.h>
@@ -26,7 +26,7 @@ static void on_message(void *user, const modes_message *mm) {
     (void)user;
     if (opt_stats) return;                                  /* dump1090.c:1803 */
     if (tracker) {                                          /* dump1090.c:1806-1809 */
-        const modes_aircraft *a = modes_tracker_update(tracker, mm, mm->sample_pos / 2000);
+        const modes_aircraft *a = modes_tracker_update(tracker, mm, MODES_STREAM_EPOCH_MS + mm->sample_pos / 2000);
         if (a && opt_sbs) {
             char line[512];
             size_t n = modes_format_sbs(mm, a, line, sizeof(line));

@@ -219,7 +219,13 @@ int    modes_parse_hex_line(const char *line, uint8_t msg[14]);
  * The per-aircraft reduce over the delivered message stream that the reference's interactive
  * mode, HTTP map and SBS port share (dump1090.c:1822-2164).  Pure host code, no GPU involved.
  * Time is supplied by the caller in milliseconds: wall clock for a live feed (what the reference
- * uses, time()/mstime()), or stream time (modes_message.sample_pos / 2000) for a file. */
+ * uses, time()/mstime()), or stream time for a file: MODES_STREAM_EPOCH_MS + sample_pos / 2000.
+ * The epoch matters: a new aircraft's odd/even CPR times start at 0, and the reference pairs two
+ * frames when their times differ by <= 10 s (dump1090.c:2122) — with a clock that starts near 0
+ * the first position frame of a file would be "paired" with the empty slot and decoded against
+ * zeros.  mstime() is ~1.7e12, so the reference never does that; neither does a stream clock
+ * that starts at the epoch below. */
+#define MODES_STREAM_EPOCH_MS 1000000000000LL
 typedef struct modes_tracker modes_tracker;
 
 /* struct aircraft (dump1090.c:112-130) */

@@ -115,7 +115,8 @@ def test_c_host_binary(checker_libs):
     # default output = the full text of displayModesMessage (dump1090.c:1314-1450): byte-identical to the
     # reference harness binary, which prints through the reference's own function
     ref_bin = C.ORACLE_DIR / "_ref" / "ref_dump1090"
-    if ref_bin.exists():
+    assert ref_bin.exists(), "oracle/_ref/ref_dump1090 missing: build it with `make oracle` where /root/reference is mounted"
+    if True:
         for flags in ([], ["--aggressive", "--no-crc-check"]):
             ours = subprocess.run([str(exe), "--ifile", f, *flags], capture_output=True, check=True).stdout
             theirs = subprocess.run([str(ref_bin), "--ifile", f, *flags], capture_output=True, check=True).stdout
@@ -128,8 +129,6 @@ def test_c_host_binary(checker_libs):
                                       "535 demodulated with zero errors", "276 with good crc"]
 
 
-@pytest.mark.skipif(not os.environ.get("MODES_TEST_UNVERIFIED"),
-                    reason="written after the round's GPU budget was spent; joins the suite once it has run on hardware")
 def test_c_host_sbs_and_json(gpu_decoder_factory, checker_libs):
     """./dump1090-b200 --sbs / --aircraft-json == the Python tracker over the same decoded messages."""
     exe = ROOT / "dump1090-b200"
@@ -138,7 +137,7 @@ def test_c_host_sbs_and_json(gpu_decoder_factory, checker_libs):
     tr = api.Tracker(1)
     lines = []
     for m in msgs:
-        g = tr.update(m, int(m.sample_pos / 2000))
+        g = tr.update(m, api.STREAM_EPOCH_MS + int(m.sample_pos / 2000))
         if g:
             lines.append(g[1])
     sbs = subprocess.run([str(exe), "--ifile", f, "--sbs"], capture_output=True, check=True, text=True).stdout

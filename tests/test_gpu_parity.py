@@ -11,11 +11,12 @@ FLAG_SETS = [dict(), dict(aggressive=1), dict(fix=0), dict(check_crc=0), dict(ch
              dict(drop_eof=1), dict(fix=0, drop_eof=1)]
 
 
-# "lean" (thread per candidate with the leaner per-bit loops) was written after the round's GPU
-# budget was spent: it is checked on the host (test_eval_serial_host.py) and joins this matrix with
-# MODES_TEST_UNVERIFIED=1 until it has been run on hardware once.
-import os
-EVAL_VARIANTS = ["serial", "warp"] + (["lean"] if os.environ.get("MODES_TEST_UNVERIFIED") else [])
+import streams as S
+
+# all three frame-evaluation kernels: thread per candidate (two codings of the per-bit loops) and warp per candidate
+EVAL_VARIANTS = ["serial", "warp", "lean"]
+# both preamble-scan kernels: "2" = modes_scan2.cu (lane = 32 positions), "1" = the round-1 row scan
+SCAN_VARIANTS = ["2", "1"]
 
 
 def _dec_kw(kw):
@@ -34,7 +35,17 @@ def _streams():
     yield "grid", synth.df17_grid(280000, 700, 5)
 
 
+def _nasty_streams():
+    """Demodulator corner cases (tests/streams.py): tri-state first bits and copied-bit runs, weak
+    pairs, and first attempts that fail exactly at j == 0 of a buffer (dump1090.c:1660)."""
+    yield "ties", S.tie_rich(11)
+    yield "ties_weak", S.tie_rich(12, levels=(0, 0, 1, 3, 30))
+    yield "retry_at_j0", S.retry_at_buffer_start()
+
+
 STREAMS = dict(_streams())
+NASTY = dict(_nasty_streams())
+ALL_STREAMS = {**STREAMS, **NASTY}
 
 
 @pytest.mark.parametrize("name", list(STREAMS))
@@ -49,22 +60,13 @@ def test_decode_matches_oracle(name, kw, gpu_decoder_factory, checker_libs):
     assert list(dec.stats().values()) == exp_stats
 
 
-@pytest.mark.parametrize("name", list(STREAMS))
-@pytest.mark.parametrize("aggressive", [0, 1])
-@pytest.mark.parametrize("variant", EVAL_VARIANTS)
-def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory, checker_libs, monkeypatch):
-    """Scan + frame-evaluation kernels: candidate set and both evaluated passes, record for record.
-    All frame-evaluation kernels (thread per candidate, the default; warp per candidate; thread per
-    candidate with the leaner per-bit loops)."""
+def _check_candidates(data, aggressive, dec):
     import torch
-    monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
-    data = STREAMS[name]
     nbuf = data.size // api.BUFFER_BYTES + 1
     padded = np.full(nbuf * api.BUFFER_BYTES, 127, dtype=np.uint8)
     padded[: data.size] = data
-    exp = C.oracle_scan_candidates(data, fix=1, aggressive=aggressive)
+    exp = C.oracle_scan_candidates(data, fix=1, aggressive=aggressive, cap=400000)
     exp_arr = np.frombuffer(b"".join(bytes(c) for c in exp), dtype=api.CANDIDATE_DTYPE)
-    dec = gpu_decoder_factory(aggressive=aggressive)
     d = torch.from_numpy(padded).cuda()
     dec.detect_device(d.data_ptr(), nbuf)
     cands, tiles = dec.detect_fetch(nbuf)
@@ -74,7 +76,54 @@ def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory,
     got = cands.view(np.uint8).reshape(-1, 56)[order]
     want = exp_arr.view(np.uint8).reshape(-1, 56)
     assert np.array_equal(got[:, :8], want[:, :8]), "candidate positions differ"
-    assert np.array_equal(got, want)
+    bad = np.nonzero((got != want).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} of {want.shape[0]} records differ, first at {bad[0]}: {got[bad[0]].tolist()} != {want[bad[0]].tolist()}"
+    return want.shape[0]
+
+
+@pytest.mark.parametrize("name", list(ALL_STREAMS))
+@pytest.mark.parametrize("aggressive", [0, 1])
+@pytest.mark.parametrize("variant", EVAL_VARIANTS)
+def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory, checker_libs, monkeypatch):
+    """Scan + frame-evaluation kernels: candidate set and both evaluated passes, record for record.
+    All frame-evaluation kernels (thread per candidate, the default; warp per candidate; thread per
+    candidate with the leaner per-bit loops), incl. the tie-rich streams and the j == 0 retries."""
+    monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
+    _check_candidates(ALL_STREAMS[name], aggressive, gpu_decoder_factory(aggressive=aggressive))
+
+
+@pytest.mark.parametrize("name", list(ALL_STREAMS))
+@pytest.mark.parametrize("scan", SCAN_VARIANTS)
+def test_scan_variants_match_oracle(name, scan, gpu_decoder_factory, checker_libs, monkeypatch):
+    """Both preamble-scan kernels find exactly the oracle's candidate positions (and records)."""
+    monkeypatch.setenv("MODES_SCAN_VARIANT", scan)
+    _check_candidates(ALL_STREAMS[name], 0, gpu_decoder_factory())
+
+
+@pytest.mark.parametrize("variant", EVAL_VARIANTS)
+def test_candidates_random_alphabets(variant, gpu_decoder_factory, checker_libs, monkeypatch):
+    """24 small streams with random amplitude alphabets, noise and saturation through the kernels
+    themselves (the same cases the host shim checks on CPU)."""
+    monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
+    total = 0
+    decs = {a: gpu_decoder_factory(aggressive=a) for a in (0, 1)}
+    for case, levels, data in S.random_alphabet_cases():
+        for aggressive in (1, 0):
+            total += _check_candidates(data, aggressive, decs[aggressive])
+    assert total > 5000
+
+
+@pytest.mark.parametrize("name", list(NASTY))
+@pytest.mark.parametrize("kw", [dict(), dict(aggressive=1), dict(check_crc=0, aggressive=1)],
+                         ids=lambda k: "-".join(f"{a}{b}" for a, b in k.items()) or "default")
+def test_nasty_streams_decode(name, kw, gpu_decoder_factory, checker_libs):
+    data = NASTY[name]
+    exp, exp_stats = C.oracle_decode(data, cap=400000, **kw)
+    dec = gpu_decoder_factory(**_dec_kw(kw))
+    got = dec.decode(data)
+    assert [m.raw_line() for m in got] == [m.hexline() for m in exp]
+    assert _fields(got) == _fields(exp)
+    assert list(dec.stats().values()) == exp_stats
 
 
 def test_magnitude_matches_oracle(gpu_decoder_factory, checker_libs):

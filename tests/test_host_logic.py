@@ -176,3 +176,52 @@ def test_parallel_shard_resolve_recovers_from_a_wrong_guess(checker_libs, capfd,
     assert "2 rounds" in capfd.readouterr().err                           # the guess was wrong, and noticed
     assert [C.msg_fields(m, with_pos=True) for m in par.take_messages()] == want
     assert par.stats() == seq.stats()
+
+
+@pytest.mark.timeout(180)
+def test_two_resolvers_on_two_threads(checker_libs):
+    """Distinct contexts are independent (include/modes_b200.h): two resolvers delivering >= 2048
+    messages each into arrays from two threads at once (the struct-building pool is shared by the
+    process) produce exactly what they produce alone.  (With the pool's job state unprotected this
+    test hangs or delivers unbuilt structs.)"""
+    import threading
+    data = synth.random_traffic(131072 * 40, 9000, 77, n_aircraft=30)
+    cands = C.oracle_scan_candidates(data, cap=400000)
+    one = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE)
+    reps = 24                                            # the same 40 buffers again and again: ~250 000 messages per call
+    arr = np.tile(one, reps)
+    arr["t"] += np.repeat(np.arange(reps, dtype=np.int64) * 40 * api.BUFFER_SAMPLES, one.size)
+    tiles = np.array([(0, arr.size)], dtype=api.TILE_DTYPE)
+
+    def run_once(r):
+        ctypes.memset(r._out, 0xEE, ctypes.sizeof(r._out))   # a struct that is never built must show
+        r.reset_state(); r.rearm_output(); r.run(arr, tiles)
+        n = r.output_count()
+        return n, hashlib.sha256(bytes(memoryview(r._out)[:n])).hexdigest()
+
+    solo = api.Resolver(check_crc=0)
+    solo.set_output_array(arr.size * 2)
+    want = run_once(solo)
+    assert want[0] >= 2048
+    rs = [api.Resolver(check_crc=0) for _ in range(2)]
+    for r in rs:
+        r.set_output_array(arr.size * 2)
+    results, errors = [[], []], []
+
+    gate = threading.Barrier(2)
+
+    def worker(k):
+        try:
+            for _ in range(12):
+                gate.wait()                              # both calls start together
+                results[k].append(run_once(rs[k]))
+        except BaseException as e:                       # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors
+    assert all(x == want for k in range(2) for x in results[k])

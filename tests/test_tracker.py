@@ -147,3 +147,31 @@ def test_tracker_ignores_bad_crc_when_checking(checker_libs):
     bad.crcok = 0
     assert api.Tracker(1).update(_as_product(bad), 1) is None and C.RefTracker(1).update(bad, 1) is None
     assert api.Tracker(0).update(_as_product(bad), 1) is not None and C.RefTracker(0).update(bad, 1) is not None
+
+
+def test_stream_clock_starts_at_the_epoch(checker_libs):
+    """A file's stream clock (sample position / 2 MHz) starts at 0: fed to the tracker as is, the
+    first airborne position of a new aircraft would be paired with the empty (time 0) slot of the
+    other parity and decoded against zeros.  With MODES_STREAM_EPOCH_MS added — what the C host
+    does — the first frame waits for its partner, exactly as under the reference's wall clock."""
+    lat, lon, icao = 47.3, 8.5, 0x4B1601
+    frames = []
+    for step, odd in enumerate((0, 1, 0)):
+        yz, xz = _cpr_encode(lat + 0.001 * step, lon, odd)
+        frames.append(_decode_frame(_position_frame(icao, 11, odd, yz, xz)))
+    stream_ms = [3, 450, 900]                                            # first seconds of a file
+    # reference behaviour under its own (wall) clock: no position after one frame, a position after two
+    ref, got = C.RefTracker(), api.Tracker()
+    for m, t in zip(frames, stream_ms):
+        r = ref.update(m, 1_700_000_000_000 + t)
+        g = got.update(_as_product(m), api.STREAM_EPOCH_MS + t)
+        rt, gt = r[0].as_tuple(), g[0].as_tuple()
+        assert (g[0].lat, g[0].lon) == (r[0].lat, r[0].lon)
+        assert g[1] == r[1]                                               # SBS line
+        if t == 3:
+            assert (g[0].lat, g[0].lon) == (0.0, 0.0)
+    assert abs(got.aircraft()[0].lat - lat) < 0.02 and abs(got.aircraft()[0].lon - lon) < 0.02
+    # the hazard itself (documented in include/modes_b200.h): a clock starting at 0 pairs the first frame with nothing
+    raw = api.Tracker()
+    g = raw.update(_as_product(frames[0]), stream_ms[0])
+    assert (g[0].lat, g[0].lon) != (0.0, 0.0)
