@@ -111,7 +111,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
-           "modes_host_free", "modes_get_kernel_times", "modes_launch_count",
+           "modes_host_free", "modes_get_kernel_times", "modes_launch_count", "modes_tile_count",
            "modes_tracker_create", "modes_tracker_destroy", "modes_tracker_update", "modes_tracker_count",
            "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
            "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl"]
@@ -182,6 +182,8 @@ def lib():
         L.modes_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
         L.modes_launch_count.restype = C.c_uint64
         L.modes_launch_count.argtypes = [C.c_void_p]
+        L.modes_tile_count.restype = C.c_size_t
+        L.modes_tile_count.argtypes = [C.c_size_t]
         _lib = L
     return _lib
 
@@ -207,7 +209,8 @@ def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, devi
 
 
 def tiles_for(n_buffers: int) -> int:
-    return n_buffers * (BUFFER_SAMPLES // TILE_SAMPLES) + 1
+    """Entries of the tile table of a batch of n_buffers reference buffers (modes_tile_count)."""
+    return int(lib().modes_tile_count(int(n_buffers)))
 
 
 def _ptr(a: np.ndarray):

@@ -28,7 +28,12 @@ struct Slot {
     modes_candidate *d_records = nullptr;
     modes_tile *d_tiles = nullptr;   uint32_t tiles_cap = 0;
     uint32_t *d_counters = nullptr;
-    uint8_t *h_halo = nullptr;       // pinned
+    // pinned carry blocks: a ring, because modes_detect_device/_host return without waiting and the
+    // next call must not rewrite a block whose host-to-device copy is still queued
+    static constexpr int kHaloRing = 8;
+    uint8_t *h_halo = nullptr;       // kHaloRing x kHaloAlloc
+    cudaEvent_t halo_ev[kHaloRing] = {};
+    unsigned halo_next = 0;
     uint32_t *h_counters = nullptr;  // pinned
     modes_candidate *h_records = nullptr; size_t h_records_cap = 0;   // pinned
     modes_tile *h_tiles = nullptr;   size_t h_tiles_cap = 0;          // pinned
@@ -106,7 +111,8 @@ int slot_init(modes_ctx *ctx, Slot &s) {
     CK(ctx, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     CK(ctx, cudaMalloc(&s.d_halo, kHaloAlloc));
     CK(ctx, cudaMalloc(&s.d_counters, 4 * sizeof(uint32_t)));
-    CK(ctx, cudaMallocHost(&s.h_halo, kHaloAlloc));
+    CK(ctx, cudaMallocHost(&s.h_halo, (size_t)kHaloAlloc * Slot::kHaloRing));
+    for (auto &e : s.halo_ev) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(ctx, cudaMallocHost(&s.h_counters, 4 * sizeof(uint32_t)));
     for (auto &e : s.ev) CK(ctx, cudaEventCreate(&e));
     return 0;
@@ -118,6 +124,7 @@ void slot_free(Slot &s) {
     cudaFree(s.d_tiles); cudaFree(s.d_counters);
     cudaFreeHost(s.h_halo); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_records); cudaFreeHost(s.h_tiles);
     for (auto &e : s.ev) if (e) cudaEventDestroy(e);
+    for (auto &e : s.halo_ev) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
     s = Slot();
 }
@@ -170,15 +177,21 @@ int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, si
            const uint8_t *carry476, modes_candidate *d_records_ext, uint32_t cap_ext, modes_tile *d_tiles_ext) {
     const uint64_t n_samples = (uint64_t)n_buffers * kBufSamples;
     if (n_samples + kHaloSamples >= (1ull << 32)) return fail(ctx, "batch too large: %zu buffers", n_buffers);
+    // caller-supplied record buffers: the slot's own position list must hold as many candidates
+    if (d_records_ext && cap_ext > s.want_cap) s.want_cap = cap_ext;
     if (slot_ensure(ctx, s, n_samples, host_iq != nullptr, d_records_ext == nullptr)) return -1;
     if (host_iq) {
         CK(ctx, cudaMemcpyAsync(s.d_iq, host_iq, n_samples * 2, cudaMemcpyHostToDevice, s.stream));
         d_iq = s.d_iq;
     }
     if ((reinterpret_cast<uintptr_t>(d_iq) & 15) != 0) return fail(ctx, "device I/Q pointer must be 16-byte aligned");
-    memset(s.h_halo, 127, kHaloAlloc);                                    // dump1090.c:344 no-signal
-    if (carry476) memcpy(s.h_halo + (kHaloBytes - MODES_CARRY_BYTES), carry476, MODES_CARRY_BYTES);
-    CK(ctx, cudaMemcpyAsync(s.d_halo, s.h_halo, kHaloAlloc, cudaMemcpyHostToDevice, s.stream));
+    const unsigned hi = s.halo_next++ % Slot::kHaloRing;
+    uint8_t *h_halo = s.h_halo + (size_t)hi * kHaloAlloc;
+    CK(ctx, cudaEventSynchronize(s.halo_ev[hi]));                         // its previous copy (8 submits ago) has left the host
+    memset(h_halo, 127, kHaloAlloc);                                      // dump1090.c:344 no-signal
+    if (carry476) memcpy(h_halo + (kHaloBytes - MODES_CARRY_BYTES), carry476, MODES_CARRY_BYTES);
+    CK(ctx, cudaMemcpyAsync(s.d_halo, h_halo, kHaloAlloc, cudaMemcpyHostToDevice, s.stream));
+    CK(ctx, cudaEventRecord(s.halo_ev[hi], s.stream));
     s.batch_iq = d_iq;
     s.n_buffers = n_buffers;
     s.own_outputs = d_records_ext == nullptr;
@@ -672,5 +685,7 @@ int modes_get_kernel_times(modes_ctx *ctx, float ms[4]) {
 }
 
 uint64_t modes_launch_count(const modes_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+size_t modes_tile_count(size_t n_buffers) { return tiles_for((uint64_t)n_buffers * kBufSamples); }
 
 }  // extern "C"

@@ -50,8 +50,14 @@ struct ScanOutputs {
     uint32_t   *counters;        // [0] candidates found (may exceed capacity), [1] overflow flag, [2]/[3] scan tile / eval chunk hand-out
 };
 
+constexpr int kScan2TileSamples = 31 * 32 * 8;                  // tile of modes_scan2.cu: 8 rows of 31 lanes x 32 positions
+
+// Scan kernel in use (MODES_SCAN_VARIANT, read per call: the tests switch it) and its tile size.
+int scan_variant();
+inline uint32_t scan_tile_samples() { return scan_variant() == 2 ? (uint32_t)kScan2TileSamples : (uint32_t)kTileSamples; }
 inline uint32_t tiles_for(uint64_t n_samples) {
-    return (uint32_t)((n_samples + kHaloSamples + kTileSamples - 1) / kTileSamples);
+    const uint32_t t = scan_tile_samples();
+    return (uint32_t)((n_samples + kHaloSamples + t - 1) / t);
 }
 
 // Kernel launchers (modes_kernels.cu).  All asynchronous on `stream`.

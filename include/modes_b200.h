@@ -105,9 +105,10 @@ typedef struct modes_candidate {
 } modes_candidate;
 
 /* Per scan tile: where its candidates sit in the candidate array.  Tiles are
- * in stream order; candidates inside a tile are in stream order. */
+ * in stream order; candidates inside a tile are in stream order.  How many positions a tile
+ * covers is the scan kernel's business: size tile tables with modes_tile_count(). */
 typedef struct modes_tile { uint32_t offset, count; } modes_tile;
-#define MODES_TILE_SAMPLES 4096
+#define MODES_TILE_SAMPLES 4096             /* tile of the round-1 scan kernel (MODES_SCAN_VARIANT=1) */
 
 /* Replaces Modes.stat_* (dump1090.c:186-195) in the order the reference prints
  * them (:2994-3003): valid_preamble, out_of_phase, demodulated, goodcrc,
@@ -156,7 +157,7 @@ int  modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples,
  * bytes preceding d_iq (host memory), or NULL at stream start (no-signal).
  * Launches the scan and frame-evaluation kernels on the context's stream and
  * returns without waiting.  d_candidates (capacity cand_capacity records) and
- * d_tiles (n_buffers*32+1 entries) are device memory supplied by the caller, or
+ * d_tiles (modes_tile_count(n_buffers) entries) are device memory supplied by the caller, or
  * NULL to use the context's own workspace. */
 int  modes_detect_device(modes_ctx *ctx, const void *d_iq, size_t n_buffers, const uint8_t *carry476,
                          void *d_candidates, size_t cand_capacity, void *d_tiles);
@@ -167,7 +168,7 @@ int  modes_detect_host(modes_ctx *ctx, const uint8_t *iq, size_t n_buffers, cons
 /* Wait for the last modes_detect_device; returns the candidate count. */
 int  modes_detect_wait(modes_ctx *ctx, uint64_t *n_candidates);
 /* Copy the last result to host memory (arrays sized by the caller from
- * modes_detect_wait's count and n_buffers*32+1 tiles). */
+ * modes_detect_wait's count and modes_tile_count(n_buffers) tiles). */
 int  modes_detect_fetch(modes_ctx *ctx, modes_candidate *candidates, modes_tile *tiles);
 
 /* The sequential half of detectModeS(): retry/skip state machine
@@ -294,6 +295,8 @@ void  modes_host_free(void *p);
 int  modes_get_kernel_times(modes_ctx *ctx, float ms[4]);
 /* Cumulative count of kernel launches issued by this context. */
 uint64_t modes_launch_count(const modes_ctx *ctx);
+/* Entries of the tile table of a batch of n_buffers reference buffers. */
+size_t modes_tile_count(size_t n_buffers);
 
 #ifdef __cplusplus
 }
