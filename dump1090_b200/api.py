@@ -19,7 +19,7 @@ LIB_PATH = _PKG / "libmodes_b200.so"
 BUFFER_BYTES = 262144
 BUFFER_SAMPLES = 131072
 CARRY_BYTES = 476
-TILE_SAMPLES = 4096
+TILE_SAMPLES = 7936                       # MODES_TILE_SAMPLES
 STREAM_EPOCH_MS = 1_000_000_000_000      # MODES_STREAM_EPOCH_MS: start of a file's stream clock for the tracker
 
 EVAL_GATE_OK, EVAL_ERRORS, EVAL_DECODED, EVAL_P2_VALID = 1, 2, 4, 8

@@ -22,7 +22,7 @@ namespace modes {
 constexpr int      kHaloSamples  = 240;
 constexpr int      kHaloBytes    = 480;
 constexpr int      kHaloAlloc    = 512;                         // + 16 bytes of "no signal" (127) after the carry: kernels read it for out-of-range chunks
-constexpr int      kTileSamples  = MODES_TILE_SAMPLES;          // one scan tile
+constexpr int      kTileSamples  = MODES_TILE_SAMPLES;          // one scan tile: 8 rows of 31 lanes x 32 positions (modes_scan2.cu)
 constexpr uint32_t kBufSamples   = MODES_BUFFER_SAMPLES;
 constexpr uint32_t kScanLimit    = kBufSamples - 2;             // j < 131070
 constexpr int      kNLutEntries  = 32769;                       // magnitude by i*i+q*q
@@ -50,22 +50,13 @@ struct ScanOutputs {
     uint32_t   *counters;        // [0] candidates found (may exceed capacity), [1] overflow flag, [2]/[3] scan tile / eval chunk hand-out
 };
 
-constexpr int kScan2TileSamples = 31 * 32 * 8;                  // tile of modes_scan2.cu: 8 rows of 31 lanes x 32 positions
-
-// Scan kernel in use (MODES_SCAN_VARIANT, read per call: the tests switch it) and its tile size.
-int scan_variant();
-inline uint32_t scan_tile_samples() { return scan_variant() == 2 ? (uint32_t)kScan2TileSamples : (uint32_t)kTileSamples; }
 inline uint32_t tiles_for(uint64_t n_samples) {
-    const uint32_t t = scan_tile_samples();
-    return (uint32_t)((n_samples + kHaloSamples + t - 1) / t);
+    return (uint32_t)((n_samples + kHaloSamples + kTileSamples - 1) / kTileSamples);
 }
 
-// Kernel launchers (modes_kernels.cu).  All asynchronous on `stream`.
+// Kernel launchers (launch_scan: modes_scan2.cu; the rest: modes_kernels.cu).  All asynchronous on `stream`.
 void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
                  cudaStream_t stream);
-// K1 as rewritten in round 2 (modes_scan2.cu): lane = 32 consecutive positions, FMA/ALU-balanced compares.
-void launch_scan2(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
-                  cudaStream_t stream);
 void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
                  modes_candidate *records, int fix_errors, int aggressive, int sm_count,
                  cudaStream_t stream);

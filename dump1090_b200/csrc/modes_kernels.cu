@@ -1,10 +1,6 @@
 // modes_kernels.cu — sm_100a kernels of the Mode S demodulator.
 //
-//   scan_kernel   (K1)  u8 I/Q -> squared magnitude -> preamble tests, fused.
-//                       Replaces computeMagnitudeVector (dump1090.c:1454-1469) and
-//                       the per-position preamble tests of detectModeS
-//                       (dump1090.c:1602-1650).  HBM-bound: 2 bytes read per sample,
-//                       nothing written but the (sparse) candidate list.
+//   (K1, the fused magnitude + preamble scan, lives in modes_scan2.cu.)
 //   eval_kernel   (K2)  one warp per candidate: bit slicing (dump1090.c:1668-1706),
 //                       delta gate (:1713-1726), phase-corrected retry (:1498-1558),
 //                       CRC syndrome (:703-742) and syndrome-table repair
@@ -35,393 +31,12 @@ namespace modes {
 
 // ------------------------------------------------------------------ helpers
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-
-// 16-byte chunk c of the virtual sample array (8 samples).  Chunks past the end
-// read as "no signal" (127,127).
-__device__ __forceinline__ uint4 load_vchunk(const BatchView &in, uint64_t c, uint64_t n_vchunks) {
-    if (c >= n_vchunks) return make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-    const uint4 *p = (c < kHaloSamples / 8) ? reinterpret_cast<const uint4 *>(in.halo) + c
-                                            : reinterpret_cast<const uint4 *>(in.body) + (c - kHaloSamples / 8);
-    return ldg_stream(p);
-}
-
 // One sample of the virtual array -> squared magnitude.
 __device__ __forceinline__ uint32_t sample_n(const BatchView &in, uint64_t v) {
     const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);
     uint32_t w = *reinterpret_cast<const uint16_t *>(p);
     uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
     return __dp4a(a, a, 0u);
-}
-
-// ------------------------------------------------------------------ K1: scan
-//
-// "Row scan".  One warp owns one tile of 4096 positions at a time and walks it in 16
-// rows of 256 positions: in row r lane l handles the 8 positions of chunk 32r+l, so
-// every load is a fully coalesced 512-byte warp read straight from HBM into registers
-// (three rows in flight per warp), with no shared-memory staging at all.  The 17-sample
-// lookahead a position needs comes from the two neighbouring lanes by shuffle (lanes 30
-// and 31 take it from the next row, which is already loaded).  With ~60 registers and
-// 2.5 KB of shared memory per warp, 32 single-warp CTAs fit an SM, which is what hides
-// the latency of the rare exact tests below.
-//
-// Arithmetic: squared magnitudes n = i*i+q*q are held two per 32-bit register as
-// 15-bit fields (n clamped to 32767, order preserving on the reachable values), so one
-// 32-bit instruction works on two positions:
-//     L + 0x7fff7fff - R  has bit 15 / bit 31 set   <=>  L > R   in the low / high half
-//     (one three-input add; no borrow or carry crosses the halves because both are <= 0x7fff)
-// The ten comparisons of dump1090.c:1602-1611 for position j reduce to
-//     min(m0,m2) > max(m1,m3)      m0 > max(m4,m5,m6)
-//     m9 > max(m6,m8)              m7 > m8
-// i.e. per pair of positions: 3 packed min, 1 packed min3, 4 adds, 2 ANDs.
-// Survivors (~1% of positions) then get the exact "high" tests (dump1090.c:1624-1642) on
-// magnitudes from the table, 32 at a time in position order; their samples are re-read
-// from L2, where the tile still sits.
-
-constexpr int kTileChunks = kTileSamples / 8;            // 512 chunks of 8 samples
-constexpr int kSurvivorCap = 512;
-constexpr int kOutCap = 256;                             // candidates per tile held back one tile
-constexpr int kRawBytes = kTileSamples * 2 + 512;         // the tile's raw I/Q + the row after it, kept for the exact tests
-constexpr int kScanWarpSmem = kRawBytes + 512 + kSurvivorCap * 2 + 2 * kOutCap * 2;
-constexpr uint32_t kK15 = 0x7fff7fffu;
-static_assert(kTileSamples == 4096, "tile = 16 rows of 32 chunks");
-
-// Two I/Q pairs -> two clamped squared magnitudes, packed (low half = first sample).
-__device__ __forceinline__ uint32_t n2_pack15(uint32_t raw) {
-    uint32_t a = __vabsdiffu4(raw, 0x7f7f7f7fu);
-    uint32_t n0 = __dp4a(a & 0xffffu, a, 0u);
-    uint32_t nt = __dp4a(a, a, 0u);
-    return __vminu2(n0 + ((nt - n0) << 16), kK15);
-}
-
-// Where a tile's samples live: interior tiles (the common case) are one flat run of the
-// body; the first tile starts in the carry block and the last one ends the batch.
-struct TileSrc {
-    const uint8_t *flat;         // address of tile sample 0 when the tile (+24 lookahead samples) is interior
-    uint64_t c0;                 // first virtual chunk of the tile
-    bool interior;
-};
-
-template <int kVariant>
-__device__ __forceinline__ uint4 load_row_chunk(const BatchView &in, const TileSrc &t, int chunk, uint64_t n_vchunks) {
-    if (t.interior) {
-        // variant 1 lets the row allocate in L1: the exact tests re-read a few of its samples
-        if (kVariant == 1) return __ldg(reinterpret_cast<const uint4 *>(t.flat) + chunk);
-        return ldg_stream(reinterpret_cast<const uint4 *>(t.flat) + chunk);
-    }
-    return load_vchunk(in, t.c0 + chunk, n_vchunks);
-}
-
-// Squared magnitude of tile sample s (0 .. 4096+23): from the warp's shared-memory copy of the
-// tile (variant 0) or re-read from global memory / L2.
-template <int kVariant>
-__device__ __forceinline__ uint32_t tile_n(const BatchView &in, const TileSrc &t, const uint8_t *raw, int s) {
-    uint32_t w;
-    if (kVariant == 0) w = *reinterpret_cast<const uint16_t *>(raw + 2 * s);
-    else if (t.interior) w = __ldg(reinterpret_cast<const uint16_t *>(t.flat) + s);
-    else return sample_n(in, t.c0 * 8 + s);
-    const uint32_t a = __vabsdiffu4(w | 0x7f7f0000u, 0x7f7f7f7fu);
-    return __dp4a(a, a, 0u);
-}
-
-// dump1090.c:1624-1642 for tile-local position s, on exact magnitudes:
-//   high = (m0+m2+m7+m9)/6;  m4, m5, m11..m14 < high
-// <=> 6*(max(m4,m5,m11..m14)+1) <= m0+m2+m7+m9, and the magnitude table is monotone in the
-// squared magnitude, so the max is taken before the lookup: five lookups instead of ten.
-template <int kVariant>
-__device__ __forceinline__ bool high_tests(const BatchView &in, const TileSrc &t, const uint8_t *raw, int s,
-                                           const uint16_t *__restrict__ lutn) {
-#define TN(d) tile_n<kVariant>(in, t, raw, s + (d))
-    const uint32_t n0 = TN(0), n2 = TN(2), n7 = TN(7), n9 = TN(9);
-    const uint32_t n4 = TN(4), n5 = TN(5), n11 = TN(11), n12 = TN(12), n13 = TN(13), n14 = TN(14);
-#undef TN
-    const uint32_t nx = max(max(max(n4, n5), max(n11, n12)), max(n13, n14));
-    const int sum = (int)__ldg(lutn + n0) + (int)__ldg(lutn + n2) + (int)__ldg(lutn + n7) + (int)__ldg(lutn + n9);
-    const int mx = __ldg(lutn + nx);
-    return 6 * (mx + 1) <= sum;
-}
-
-// One lane's survivors (bits of acc[4], bit i of word g = tile position 128*lane+32g+i) -> the
-// slots [excl, excl+cnt) of the tile-ordered survivor sequence; writes those that fall in
-// [round, round+kSurvivorCap) to the list.
-__device__ __forceinline__ void list_survivors(const uint32_t acc[4], uint32_t excl, uint32_t round, uint16_t *surv,
-                                               int lane) {
-    uint32_t slot = excl - round;
-#pragma unroll
-    for (int gq = 0; gq < 4; gq++)
-        for (uint32_t r = acc[gq]; r; r &= r - 1) {
-            if (slot < (uint32_t)kSurvivorCap) surv[slot] = (uint16_t)(128 * lane + 32 * gq + __ffs(r) - 1);
-            slot++;
-        }
-}
-
-// Copy a finished tile's candidate list (tile-local positions, position order) to its slot in the
-// global candidate array and record the tile.  `base0` is the slot claimed one tile earlier.
-__device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t *olist, uint32_t tile, uint32_t base0,
-                                          uint32_t total, int lane) {
-    const uint32_t base = __shfl_sync(0xffffffffu, base0, 0);
-    const uint32_t v0 = tile * (uint32_t)kTileSamples;
-    for (uint32_t i = lane; i < total; i += 32)
-        if (base + i < out.cand_capacity) out.cand_v[base + i] = v0 + olist[i];
-    if (lane == 0) {
-        uint32_t stored = total;
-        if (base + total > out.cand_capacity) {
-            stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
-            out.counters[1] = 1;
-        }
-        modes_tile tl; tl.offset = base; tl.count = stored;
-        out.tiles[tile] = tl;
-    }
-}
-
-// One row of the tile: positions 256r+8*lane .. +7.  `Pc` = this lane's packed squared
-// magnitudes for row r, `xn` = raw chunk of row r+1 (becomes Pc; kept in shared memory for the
-// exact tests).
-#define MODES_SCAN_ROW(r_, xn)                                                                                     \
-    {                                                                                                              \
-        const int r = (r_);                                                                                        \
-        uint32_t Pn[4];                                                                                            \
-        Pn[0] = n2_pack15(xn.x); Pn[1] = n2_pack15(xn.y); Pn[2] = n2_pack15(xn.z); Pn[3] = n2_pack15(xn.w);        \
-        if (kVariant == 0) reinterpret_cast<uint4 *>(raw)[32 * (r + 1) + lane] = xn;                               \
-        uint32_t P[9];                                                                                             \
-        P[0] = Pc[0]; P[1] = Pc[1]; P[2] = Pc[2]; P[3] = Pc[3];                                                    \
-        _Pragma("unroll") for (int k = 0; k < 4; k++)                                                              \
-            P[4 + k] = __shfl_sync(0xffffffffu, lane == 0 ? Pn[k] : Pc[k], (lane + 1) & 31);                       \
-        P[8] = __shfl_sync(0xffffffffu, lane < 2 ? Pn[0] : Pc[0], (lane + 2) & 31);                                \
-        uint32_t T[4];                                                                                             \
-        _Pragma("unroll") for (int u = 0; u < 4; u++) {                                                            \
-            const uint32_t S0 = __byte_perm(P[u], P[u + 1], 0x5432), S1 = __byte_perm(P[u + 1], P[u + 2], 0x5432); \
-            const uint32_t S2 = __byte_perm(P[u + 2], P[u + 3], 0x5432);                                           \
-            const uint32_t S3 = __byte_perm(P[u + 3], P[u + 4], 0x5432), S4 = __byte_perm(P[u + 4], P[u + 5], 0x5432); \
-            const uint32_t A = __vminu2(P[u], P[u + 1]);             /* min(m0, m2)     */                         \
-            const uint32_t B = __vmaxu2(S0, S1);                     /* max(m1, m3)     */                         \
-            const uint32_t W = __vimax3_u16x2(P[u + 2], S2, P[u + 3]); /* max(m4, m5, m6) */                       \
-            const uint32_t E = __vmaxu2(P[u + 3], P[u + 4]);         /* max(m6, m8)     */                         \
-            /* L + 0x7fff - R per 16-bit half: bit 15 set <=> L > R; no borrow or carry between halves */         \
-            const uint32_t D1 = A + kK15 - B, D2 = P[u] + kK15 - W, D3 = S4 + kK15 - E, D4 = S3 + kK15 - P[u + 4]; \
-            T[u] = D1 & D2 & D3 & D4;                           /* bit 15 / 31: position 2u / 2u+1 passes */       \
-        }                                                                                                          \
-        const uint32_t X = __byte_perm(T[0], T[1], 0x7531), Y = __byte_perm(T[2], T[3], 0x7531);                   \
-        const uint32_t lo4 = ((X & 0x80808080u) * 0x00204081u) >> 28;                                              \
-        const uint32_t hi4 = ((Y & 0x80808080u) * 0x00204081u) >> 24;                                              \
-        rowmask[32 * r + lane] = (uint8_t)(lo4 | (hi4 & 0xf0u));                                                   \
-        Pc[0] = Pn[0]; Pc[1] = Pn[1]; Pc[2] = Pn[2]; Pc[3] = Pn[3];                                                \
-    }
-
-__device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, uint64_t n_vchunks) {
-    TileSrc ts;
-    ts.c0 = (uint64_t)g * kTileChunks;
-    ts.interior = ts.c0 >= kHaloSamples / 8 && ts.c0 + kTileChunks + 3 <= n_vchunks;
-    ts.flat = in.body + 16 * (ts.c0 - kHaloSamples / 8);
-    return ts;
-}
-
-// kVariant 1 (default): nothing is staged; the rows are loaded through L1 and the exact tests
-// re-read their few samples from it (measured DRAM traffic 1.015x the input), 64 registers and
-// 2.5 KB of shared memory per warp -> 32 warps/SM.  kVariant 0 keeps a copy of the tile's raw bytes
-// in shared memory instead (traffic 1.00x, 19 warps/SM, ~10 % slower); MODES_SCAN_VARIANT=0 selects it.
-template <int kVariant>
-__global__ void __launch_bounds__(32, kVariant == 1 ? 32 : 19)
-scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr int kRaw = kVariant == 0 ? kRawBytes : 0;
-    uint8_t *raw = smem;                                                             // tile's raw I/Q (17 rows), chunk order
-    uint8_t *rowmask = smem + kRaw;                                                  // 512 flag bytes: byte = position/8
-    uint16_t *surv = reinterpret_cast<uint16_t *>(smem + kRaw + 512);                // survivor positions
-    uint16_t *olist0 = reinterpret_cast<uint16_t *>(smem + kRaw + 512 + kSurvivorCap * 2);  // 2 x candidate lists
-    uint32_t pend_tile = 0xffffffffu, pend_base = 0, pend_total = 0, pend_buf = 0;
-
-    const int lane = threadIdx.x;
-    const uint64_t n_vchunks = (in.n_samples + kHaloSamples) / 8;
-    const uint64_t t_end = in.n_samples;
-
-    // rows 0..3 of the first tile
-    uint32_t g = blockIdx.x;
-    if (g >= n_tiles) return;
-    TileSrc ts = tile_source(in, g, n_vchunks);
-    uint4 x0 = load_row_chunk<kVariant>(in, ts, lane, n_vchunks), x1 = load_row_chunk<kVariant>(in, ts, 32 + lane, n_vchunks);
-    uint4 x2 = load_row_chunk<kVariant>(in, ts, 64 + lane, n_vchunks), x3 = load_row_chunk<kVariant>(in, ts, 96 + lane, n_vchunks);
-
-    // Tiles are handed out dynamically (first come, first served from a global counter, after one
-    // static tile per warp): warps finish within a tile of each other instead of a stride's worth.
-    // The next index is requested a whole tile ahead, so the atomic's latency is never waited for.
-    uint32_t g_ahead = 0;
-    if (lane == 0) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
-    for (int it = 0; g < n_tiles; ++it) {
-        const int cur = it & 1;
-
-        // ---- 16 rows of 32 chunks.  x0..x3 hold rows 4k..4k+3 on entry of group k; the four loads
-        // of the next group are issued together at the top of the group (one scoreboard group,
-        // a full group of arithmetic between issue and first use).
-        uint32_t Pc[4];
-        Pc[0] = n2_pack15(x0.x); Pc[1] = n2_pack15(x0.y); Pc[2] = n2_pack15(x0.z); Pc[3] = n2_pack15(x0.w);
-        if (kVariant == 0) reinterpret_cast<uint4 *>(raw)[lane] = x0;
-#pragma unroll 1
-        for (int rr = 0; rr < 16; rr += 4) {
-            const uint4 pad = make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-            uint4 y0 = pad, y1 = pad, y2 = pad, y3 = pad;       // rows rr+4 .. rr+7
-            if (rr + 4 < 16) {
-                y0 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 4) + lane, n_vchunks);
-                y1 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 5) + lane, n_vchunks);
-                y2 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 6) + lane, n_vchunks);
-                y3 = load_row_chunk<kVariant>(in, ts, 32 * (rr + 7) + lane, n_vchunks);
-            } else if (lane < 3) {
-                y0 = load_row_chunk<kVariant>(in, ts, 32 * 16 + lane, n_vchunks);   // the row after the tile: lookahead only
-            }
-            MODES_SCAN_ROW(rr + 0, x1)
-            MODES_SCAN_ROW(rr + 1, x2)
-            MODES_SCAN_ROW(rr + 2, x3)
-            MODES_SCAN_ROW(rr + 3, y0)
-            x1 = y1; x2 = y2; x3 = y3;
-        }
-
-        // ---- start the next tile's first four rows now; they arrive while this tile is finished
-        const uint32_t g_next = __shfl_sync(0xffffffffu, g_ahead, 0);
-        if (lane == 0 && g_next < n_tiles) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
-        const TileSrc ts_cur = ts;
-        if (g_next < n_tiles) {
-            ts = tile_source(in, g_next, n_vchunks);
-            x0 = load_row_chunk<kVariant>(in, ts, lane, n_vchunks); x1 = load_row_chunk<kVariant>(in, ts, 32 + lane, n_vchunks);
-            x2 = load_row_chunk<kVariant>(in, ts, 64 + lane, n_vchunks); x3 = load_row_chunk<kVariant>(in, ts, 96 + lane, n_vchunks);
-        }
-        __syncwarp();
-        // lane j now takes the 128 consecutive positions [128j, 128j+128) of the tile
-        uint32_t acc[4];
-        {
-            const uint4 m4 = reinterpret_cast<const uint4 *>(rowmask)[lane];
-            acc[0] = m4.x; acc[1] = m4.y; acc[2] = m4.z; acc[3] = m4.w;
-        }
-
-        // ---- write out the PREVIOUS tile's candidates: its slot in the global array (one atomic
-        // per tile) was claimed before this tile's rows were scanned, so the round trip is hidden
-        if (pend_tile != 0xffffffffu) {
-            emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
-            pend_tile = 0xffffffffu;
-        }
-
-        // ---- positions the reference never tests (dump1090.c:1593): j >= 131070 are the first two
-        // positions of every 32nd tile (v = t+2); the last tile ends at t = N-1
-        const uint32_t v_tile = g * (uint32_t)kTileSamples;
-        if ((g & 31u) == 0 && lane == 0) acc[0] &= ~3u;
-        if (t_end + 2 - v_tile < (uint64_t)kTileSamples) {
-            const int s_max = (int)(t_end + 2 - v_tile);
-#pragma unroll
-            for (int gq = 0; gq < 4; gq++) {
-                const int lo_pos = 128 * lane + 32 * gq;
-                if (lo_pos >= s_max) acc[gq] = 0;
-                else if (lo_pos + 32 > s_max) acc[gq] &= (1u << (s_max - lo_pos)) - 1u;
-            }
-        }
-
-        // ---- survivors of the ten comparisons (~1% of positions) get the exact "high" tests,
-        // 32 at a time in position order; passes are appended to this tile's candidate list
-        const uint32_t cnt = __popc(acc[0]) + __popc(acc[1]) + __popc(acc[2]) + __popc(acc[3]);
-        uint32_t incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += o;
-        }
-        const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31);
-        uint16_t *olist = olist0 + kOutCap * cur;
-        uint32_t n_out = 0;
-        bool dense = n_surv > (uint32_t)kSurvivorCap;
-        if (!dense) {
-            list_survivors(acc, incl - cnt, 0, surv, lane);
-            __syncwarp();
-            for (uint32_t i0 = 0; i0 < n_surv; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                const int spos = i < n_surv ? surv[i] : 0;
-                const bool pass = i < n_surv && high_tests<kVariant>(in, ts_cur, raw, spos, lutn);
-                const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-                const uint32_t slot = n_out + __popc(bal & ((1u << lane) - 1u));
-                if (pass && slot < (uint32_t)kOutCap) olist[slot] = (uint16_t)spos;
-                n_out += __popc(bal);
-            }
-            dense = n_out > (uint32_t)kOutCap;
-        }
-        if (!dense) {
-            // claim the slot now, copy the list one tile later
-            pend_base = 0;
-            if (lane == 0 && n_out) pend_base = atomicAdd(&out.counters[0], n_out);
-            pend_total = n_out; pend_tile = g; pend_buf = cur;
-        } else {
-            // pathological density: count, claim, then write straight to the global array
-            uint32_t total = 0;
-            for (int pass_no = 0; pass_no < 2; pass_no++) {
-                uint32_t base = 0, run = 0;
-                if (pass_no == 1) {
-                    if (lane == 0 && total) base = atomicAdd(&out.counters[0], total);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                }
-                for (uint32_t round = 0; round < n_surv; round += kSurvivorCap) {
-                    __syncwarp();
-                    list_survivors(acc, incl - cnt, round, surv, lane);
-                    __syncwarp();
-                    const uint32_t n_here = min(n_surv - round, (uint32_t)kSurvivorCap);
-                    for (uint32_t i0 = 0; i0 < n_here; i0 += 32) {
-                        const uint32_t i = i0 + lane;
-                        const int spos = i < n_here ? surv[i] : 0;
-                        const bool pass = i < n_here && high_tests<kVariant>(in, ts_cur, raw, spos, lutn);
-                        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-                        if (pass_no == 1 && pass) {
-                            const uint32_t idx = base + run + __popc(bal & ((1u << lane) - 1u));
-                            if (idx < out.cand_capacity) out.cand_v[idx] = v_tile + spos;
-                        }
-                        run += __popc(bal);
-                    }
-                }
-                if (pass_no == 0) total = run;
-                else if (lane == 0) {
-                    uint32_t stored = total;
-                    if (base + total > out.cand_capacity) {
-                        stored = base < out.cand_capacity ? out.cand_capacity - base : 0;
-                        out.counters[1] = 1;
-                    }
-                    modes_tile tl; tl.offset = base; tl.count = stored;
-                    out.tiles[g] = tl;
-                }
-            }
-        }
-        __syncwarp();                                    // raw, rowmask and the lists are reused by the next tile
-        g = g_next;
-    }
-    if (pend_tile != 0xffffffffu) emit_tile(out, olist0 + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
-}
-
-template <int kVariant>
-static void launch_scan_variant(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
-                                cudaStream_t stream) {
-    constexpr int smem = kScanWarpSmem - (kVariant == 0 ? 0 : kRawBytes);
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-        cudaFuncSetAttribute(scan_kernel<kVariant>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<kVariant>, 32, smem) != cudaSuccess ||
-            ctas_per_sm < 1)
-            ctas_per_sm = 16;
-    }
-    const uint32_t n_tiles = (uint32_t)((in.n_samples + kHaloSamples + kTileSamples - 1) / kTileSamples);
-    uint32_t grid = (uint32_t)(sm_count * ctas_per_sm);  // persistent single-warp CTAs, all resident
-    if (grid > n_tiles) grid = n_tiles;
-    scan_kernel<kVariant><<<grid, 32, smem, stream>>>(in, tab.lutn, out, n_tiles);
-}
-
-int scan_variant() {
-    const char *e = getenv("MODES_SCAN_VARIANT");
-    return e ? atoi(e) : 1;
-}
-
-void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count,
-                 cudaStream_t stream) {
-    const int variant = scan_variant();
-    if (variant == 2) launch_scan2(in, tab, out, sm_count, stream);
-    else if (variant == 0) launch_scan_variant<0>(in, tab, out, sm_count, stream);
-    else launch_scan_variant<1>(in, tab, out, sm_count, stream);
 }
 
 // ------------------------------------------------------- K2: frame evaluation

@@ -413,7 +413,7 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
                     ResolveState g = st;
                     g.cur_buffer = -1; g.next_j = 0;
                     const size_t nt = n_tiles[k - 1];
-                    size_t tail = nt / 16 > 256 ? nt / 16 : 256;
+                    size_t tail = nt / 16 > 128 ? nt / 16 : 128;       // at least ~1 M samples (half a second of stream)
                     if (tail > nt) tail = nt;
                     runs[k].deliveries.clear();
                     judge_tiles(g, cfg, cands[k - 1], tiles[k - 1] + (nt - tail), tail, buffer_base[k - 1], runs[k].deliveries);

@@ -31,7 +31,7 @@
 namespace modes {
 namespace {
 
-constexpr int kRows = kScan2TileSamples / (31 * 32);     // rows per tile: 8
+constexpr int kRows = kTileSamples / (31 * 32);          // rows per tile: 8
 constexpr int kRowFresh = 31 * 32;                       // positions a row decides
 constexpr int kTile = kRows * kRowFresh;                 // 7936 positions
 constexpr int kRowStrideChunks = kRowFresh / 8;          // 124 16-byte chunks between row starts
@@ -41,7 +41,7 @@ constexpr int kEntryCap = 256;                           // non-empty flag words
 constexpr int kSurvivorCap = 512;                        // survivors per tile the fast path holds (dense path: per round)
 constexpr int kOutCap = 256;                             // candidates per tile held back one tile
 constexpr int kExactRounds = 3;                          // rounds of 32 exact tests whose loads are in flight together
-static_assert(kTile == kScan2TileSamples && kRows % 4 == 0 && 32 % kRows == 0, "tile geometry");
+static_assert(kTile == kTileSamples && kRows % 4 == 0 && 32 % kRows == 0, "tile geometry");
 
 struct TileSrc {
     const uint4 *flat;           // chunk 0 of the tile when every row lies inside the body
@@ -59,10 +59,12 @@ __device__ __forceinline__ TileSrc tile_source(const BatchView &in, uint32_t g, 
 
 // Chunk c of the virtual sample array (carry block, then the body); chunks past the end read as
 // "no signal" (127,127).  Only the first and the last tiles of a batch come here.
-__device__ __noinline__ uint4 load_vchunk(const BatchView &in, uint64_t c, uint64_t n_vchunks) {
+// (Out-of-line helpers take plain values: a reference to a kernel-parameter struct or to a register
+// array would force a copy in local memory, read back through L1 in the hot path.)
+__device__ __noinline__ uint4 load_vchunk(const uint8_t *body, const uint8_t *halo, uint64_t c, uint64_t n_vchunks) {
     if (c >= n_vchunks) return make_uint4(0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu, 0x7f7f7f7fu);
-    const uint4 *p = (c < kHaloSamples / 8) ? reinterpret_cast<const uint4 *>(in.halo) + c
-                                            : reinterpret_cast<const uint4 *>(in.body) + (c - kHaloSamples / 8);
+    const uint4 *p = (c < kHaloSamples / 8) ? reinterpret_cast<const uint4 *>(halo) + c
+                                            : reinterpret_cast<const uint4 *>(body) + (c - kHaloSamples / 8);
     return __ldg(p);
 }
 
@@ -76,24 +78,26 @@ __device__ __forceinline__ void load_row(const BatchView &in, const TileSrc &t, 
     } else {
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
-            const uint4 v = load_vchunk(in, t.c0 + chunk + k, n_vchunks);
+            const uint4 v = load_vchunk(in.body, in.halo, t.c0 + chunk + k, n_vchunks);
             if (k == 0) x[0] = v; else if (k == 1) x[1] = v; else if (k == 2) x[2] = v; else x[3] = v;
         }
     }
 }
 
-// Ask L2 for row r of a tile (2 KB) with one bulk-prefetch instruction.  Issued three rows ahead
+// Ask L2 for rows r, r+1 of a tile (4 KB) with one bulk-prefetch instruction.  Issued four rows ahead
 // (a few microseconds: prefetched further ahead, lines were evicted again before their use and
 // DRAM traffic went up by 70 %), it turns the row load's DRAM latency into an L2 hit, which the
 // one-row-ahead register reload covers.
-constexpr int kPrefetchRows = 3;
-__device__ __forceinline__ void prefetch_row_l2(const TileSrc &t, int r) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.flat + kRowStrideChunks * r), "r"(2048) : "memory");
+constexpr int kPrefetchRows = 4;                         // = two steps of two rows
+__device__ __forceinline__ void prefetch_rows2_l2(const TileSrc &t, int r) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(t.flat + kRowStrideChunks * r), "r"(16 * kRowStrideChunks + 2048) : "memory");
 }
 
+// Squared magnitude of one sample (I in byte 0, Q in byte 1, upper bytes zero: they come out of
+// the byte-wise |x - 127| as 127 each, which the dot product's addend takes off again).
 __device__ __forceinline__ uint32_t n_of(uint32_t iq16) {
-    const uint32_t a = __vabsdiffu4(iq16 | 0x7f7f0000u, 0x7f7f7f7fu);
-    return __dp4a(a, a, 0u);
+    const uint32_t a = __vabsdiffu4(iq16, 0x7f7f7f7fu);
+    return __dp4a(a, a, (uint32_t)(-2 * 127 * 127));
 }
 
 // dump1090.c:1624-1642 on exact magnitudes, given the squared magnitudes of m0, m2, m7, m9 and the
@@ -117,20 +121,21 @@ __device__ __forceinline__ bool high_tests_at(const uint16_t *__restrict__ p, co
 }
 
 // The same for the first and last tiles of a batch (carry block, end of data), sample by sample.
-__device__ __noinline__ bool high_tests_edge(const BatchView &in, uint64_t v, const uint16_t *__restrict__ lutn) {
+__device__ __noinline__ bool high_tests_edge(const uint8_t *body, const uint8_t *halo, uint64_t n_samples, uint64_t v,
+                                             const uint16_t *__restrict__ lutn) {
     uint32_t n[15];
 #pragma unroll
     for (int d = 0; d < 15; d++) {
         const uint64_t vd = v + d;
-        const uint8_t *p = (vd < (uint64_t)kHaloSamples) ? in.halo + 2 * vd : in.body + 2 * (vd - kHaloSamples);
-        n[d] = n_of(vd < in.n_samples + kHaloSamples ? *reinterpret_cast<const uint16_t *>(p) : 0x7f7fu);
+        const uint8_t *p = (vd < (uint64_t)kHaloSamples) ? halo + 2 * vd : body + 2 * (vd - kHaloSamples);
+        n[d] = n_of(vd < n_samples + kHaloSamples ? *reinterpret_cast<const uint16_t *>(p) : 0x7f7fu);
     }
     return high_rule(n[0], n[2], n[7], n[9], max(max(max(n[4], n[5]), max(n[11], n[12])), max(n[13], n[14])), lutn);
 }
 
 __device__ __forceinline__ bool high_tests(const BatchView &in, const TileSrc &t, int s, const uint16_t *__restrict__ lutn) {
     if (t.interior) return high_tests_at(reinterpret_cast<const uint16_t *>(t.flat) + s, lutn);
-    return high_tests_edge(in, t.c0 * 8 + (uint64_t)s, lutn);
+    return high_tests_edge(in.body, in.halo, in.n_samples, t.c0 * 8 + (uint64_t)s, lutn);
 }
 
 // This lane's survivors (bit i of w[q] = tile position base + 32q + i) -> the slots [excl, excl+cnt)
@@ -167,16 +172,32 @@ __device__ __forceinline__ void emit_tile(const ScanOutputs &out, const uint16_t
 // A tile with more survivors or candidates than the fast path's buffers hold (periodic input that
 // makes nearly every position a preamble): count, claim a slot in the candidate array, then write
 // the candidates straight to it, survivors listed kSurvivorCap at a time.  Out of line: never
-// executed on real traffic, and the hot loop should stay small.
-__device__ __noinline__ void dense_tile(const BatchView &in, const TileSrc &ts, const uint16_t *__restrict__ lutn,
-                                        const ScanOutputs &out, uint32_t g, const uint32_t w[kRows], int base, uint32_t excl,
-                                        uint32_t n_surv, uint16_t *surv, int lane) {
+// executed on real traffic, and the hot loop should stay small.  The (validity-masked) flag words
+// are handed over in shared memory, lane j's at s_words[kRows*j ..].
+__device__ __noinline__ void dense_tile(const uint8_t *body, const uint8_t *halo, uint64_t n_samples, uint64_t n_vchunks,
+                                        const uint16_t *__restrict__ lutn, uint32_t *cand_v, uint32_t cand_capacity,
+                                        modes_tile *tiles, uint32_t *counters, uint32_t g, const uint32_t *s_words,
+                                        uint16_t *surv, int lane) {
+    const BatchView in{body, halo, n_samples};
+    const TileSrc ts = tile_source(in, g, n_vchunks);
+    uint32_t w[kRows];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int q = 0; q < kRows; q++) { w[q] = s_words[kRows * lane + q]; cnt += __popc(w[q]); }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const uint32_t n_surv = __shfl_sync(0xffffffffu, incl, 31), excl = incl - cnt;
+    const int base = kRowFresh * ((kRows * lane) >> 5) + 32 * ((kRows * lane) & 31);
     const uint32_t v_tile = g * (uint32_t)kTile;
     uint32_t total = 0;
     for (int pass_no = 0; pass_no < 2; pass_no++) {
         uint32_t gbase = 0, run = 0;
         if (pass_no == 1) {
-            if (lane == 0 && total) gbase = atomicAdd(&out.counters[0], total);
+            if (lane == 0 && total) gbase = atomicAdd(&counters[0], total);
             gbase = __shfl_sync(0xffffffffu, gbase, 0);
         }
         for (uint32_t round = 0; round < n_surv; round += kSurvivorCap) {
@@ -191,7 +212,7 @@ __device__ __noinline__ void dense_tile(const BatchView &in, const TileSrc &ts, 
                 const uint32_t bal = __ballot_sync(0xffffffffu, pass);
                 if (pass_no == 1 && pass) {
                     const uint32_t idx = gbase + run + __popc(bal & ((1u << lane) - 1u));
-                    if (idx < out.cand_capacity) out.cand_v[idx] = v_tile + spos;
+                    if (idx < cand_capacity) cand_v[idx] = v_tile + spos;
                 }
                 run += __popc(bal);
             }
@@ -199,20 +220,20 @@ __device__ __noinline__ void dense_tile(const BatchView &in, const TileSrc &ts, 
         if (pass_no == 0) total = run;
         else if (lane == 0) {
             uint32_t stored = total;
-            if (gbase + total > out.cand_capacity) {
-                stored = gbase < out.cand_capacity ? out.cand_capacity - gbase : 0;
-                out.counters[1] = 1;
+            if (gbase + total > cand_capacity) {
+                stored = gbase < cand_capacity ? cand_capacity - gbase : 0;
+                counters[1] = 1;
             }
             modes_tile tl; tl.offset = gbase; tl.count = stored;
-            out.tiles[g] = tl;
+            tiles[g] = tl;
         }
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(32, 20)
-scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles, uint32_t one,
-             uint32_t minus_one) {
+__global__ void __launch_bounds__(32, 16)
+scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, uint32_t n_tiles, uint32_t one,
+             uint32_t minus_one, uint32_t c65536) {
     __shared__ __align__(16) uint32_t s_mask[kRows * 32];
     __shared__ __align__(16) uint2 s_entry[kEntryCap];                // non-empty flag words: {word, position of bit 0 | first survivor slot << 16}
     __shared__ __align__(16) uint16_t s_surv[kSurvivorCap];           // survivor positions, position order
@@ -227,47 +248,63 @@ scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, u
     uint32_t g = blockIdx.x;
     if (g >= n_tiles) return;
     TileSrc ts = tile_source(in, g, n_vchunks);
-    uint4 x[4];                                           // the row in flight / being packed
+    uint4 x[8];                                           // the two rows in flight / being packed
     load_row(in, ts, 0, lane, n_vchunks, x);
+    load_row(in, ts, 1, lane, n_vchunks, x + 4);
 
     // Tiles are handed out first come, first served (after one static tile per warp); the index
     // is requested a whole tile before it is needed, so the atomic's latency is never waited for.
+    // (The returned counter is used untouched until the next tile: any arithmetic on it here would
+    // wait for the atomic's round trip.)
     uint32_t g_ahead = 0;
-    if (lane == 0) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
+    if (lane == 0) g_ahead = atomicAdd(&out.counters[2], 1u);
 
     for (int it = 0; g < n_tiles; ++it) {
         const int cur = it & 1;
         const TileSrc ts_cur = ts;
-        const uint32_t g_next = __shfl_sync(0xffffffffu, g_ahead, 0);
+        const uint32_t g_next = gridDim.x + __shfl_sync(0xffffffffu, g_ahead, 0);
         // Both atomics of a tile are issued here, with the whole row loop between them and their
         // consumers: the request for the tile after next, and the previous tile's slot in the
         // candidate array (its list is copied out after this tile's rows).
         if (lane == 0) {
-            if (g_next < n_tiles) g_ahead = gridDim.x + atomicAdd(&out.counters[2], 1u);
+            if (g_next < n_tiles) g_ahead = atomicAdd(&out.counters[2], 1u);
             if (pend_tile != 0xffffffffu && pend_total) pend_base = atomicAdd(&out.counters[0], pend_total);
         }
         if (g_next < n_tiles) ts = tile_source(in, g_next, n_vchunks);
 
-        // ---- the rows.  The registers a row arrived in are reloaded with the next row as soon as
-        // it is packed: that load has the whole comparison phase to complete.
+        // ---- the rows, two at a time (the halves of a register hold the same sample of both rows).
+        // The registers the rows arrived in are reloaded with the next two as soon as they are
+        // packed: that load has the whole comparison phase to complete.
 #pragma unroll 1
-        for (int r = 0; r < kRows; r++) {
-            uint32_t P[scan2::kLaneWords + scan2::kLookWords];
+        for (int r = 0; r < kRows; r += 2) {
+            uint32_t X[32 + scan2::kPairLook];
 #pragma unroll
             for (int p = 0; p < 4; p++) {
-                P[4 * p + 0] = scan2::npack(x[p].x); P[4 * p + 1] = scan2::npack(x[p].y);
-                P[4 * p + 2] = scan2::npack(x[p].z); P[4 * p + 3] = scan2::npack(x[p].w);
+                scan2::npack2(x[p].x, x[4 + p].x, c65536, minus_one, X[8 * p + 0], X[8 * p + 1]);
+                scan2::npack2(x[p].y, x[4 + p].y, c65536, minus_one, X[8 * p + 2], X[8 * p + 3]);
+                scan2::npack2(x[p].z, x[4 + p].z, c65536, minus_one, X[8 * p + 4], X[8 * p + 5]);
+                scan2::npack2(x[p].w, x[4 + p].w, c65536, minus_one, X[8 * p + 6], X[8 * p + 7]);
             }
-            if (r + 1 < kRows) load_row(in, ts_cur, r + 1, lane, n_vchunks, x);
+            // Copy out the PREVIOUS tile's candidates here: its slot was claimed two steps ago, and
+            // every older load has just been consumed, so nothing this waits on is still in flight.
+            if (r == 2 && pend_tile != 0xffffffffu) {
+                emit_tile(out, s_olist + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
+                pend_tile = 0xffffffffu;
+            }
+            if (r + 2 < kRows) load_row(in, ts_cur, r + 2, lane, n_vchunks, x);
             else if (g_next < n_tiles) load_row(in, ts, 0, lane, n_vchunks, x);
+            if (r + 2 < kRows) load_row(in, ts_cur, r + 3, lane, n_vchunks, x + 4);
+            else if (g_next < n_tiles) load_row(in, ts, 1, lane, n_vchunks, x + 4);
             if (lane == 0) {
-                if (r + kPrefetchRows < kRows) { if (ts_cur.interior) prefetch_row_l2(ts_cur, r + kPrefetchRows); }
-                else if (g_next < n_tiles && ts.interior) prefetch_row_l2(ts, r + kPrefetchRows - kRows);
+                if (r + kPrefetchRows < kRows) { if (ts_cur.interior) prefetch_rows2_l2(ts_cur, r + kPrefetchRows); }
+                else if (g_next < n_tiles && ts.interior) prefetch_rows2_l2(ts, r + kPrefetchRows - kRows);
             }
 #pragma unroll
-            for (int k = 0; k < scan2::kLookWords; k++) P[16 + k] = __shfl_down_sync(0xffffffffu, P[k], 1);
-            const uint32_t mask = scan2::row_mask(P, one, minus_one);
-            s_mask[32 * r + lane] = lane == 31 ? 0u : mask;          // lane 31's positions belong to the next row
+            for (int k = 0; k < scan2::kPairLook; k++) X[32 + k] = __shfl_down_sync(0xffffffffu, X[k], 1);
+            uint32_t ma, mb;
+            scan2::rows2_mask(X, one, minus_one, ma, mb);
+            s_mask[32 * r + lane] = lane == 31 ? 0u : ma;            // lane 31's positions belong to the next row
+            s_mask[32 * r + 32 + lane] = lane == 31 ? 0u : mb;
         }
         __syncwarp();
         // lane j now takes words kRows*j .. kRows*j + kRows-1 = 32*kRows consecutive positions of one row
@@ -278,12 +315,6 @@ scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, u
             w[4 * q4 + 0] = m4.x; w[4 * q4 + 1] = m4.y; w[4 * q4 + 2] = m4.z; w[4 * q4 + 3] = m4.w;
         }
         const int base = kRowFresh * ((kRows * lane) >> 5) + 32 * ((kRows * lane) & 31);   // tile position of bit 0 of w[0]
-
-        // ---- write out the PREVIOUS tile's candidates (slot claimed before this tile's rows)
-        if (pend_tile != 0xffffffffu) {
-            emit_tile(out, s_olist + kOutCap * pend_buf, pend_tile, pend_base, pend_total, lane);
-            pend_tile = 0xffffffffu;
-        }
 
         // ---- positions the reference never tests (dump1090.c:1593): j >= 131070, i.e. the first
         // two positions v = 131072k, 131072k+1 of every buffer (v = t+2); the batch ends at t = N-1
@@ -384,7 +415,7 @@ scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, u
                 } else {
 #pragma unroll
                     for (int k = 0; k < kExactRounds; k++)
-                        pass[k] = high_tests_edge(in, ts_cur.c0 * 8 + (uint64_t)spos[k], lutn);
+                        pass[k] = high_tests_edge(in.body, in.halo, in.n_samples, ts_cur.c0 * 8 + (uint64_t)spos[k], lutn);
                 }
 #pragma unroll
                 for (int k = 0; k < kExactRounds; k++) {
@@ -400,7 +431,12 @@ scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, u
         if (!dense) {
             pend_total = n_out; pend_tile = g; pend_buf = cur;       // its slot is claimed at the top of the next tile
         } else {
-            dense_tile(in, ts_cur, lutn, out, g, w, base, (incl >> 16) - cnt, n_surv, s_surv, lane);
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < kRows; q++) s_mask[kRows * lane + q] = w[q];       // as masked above
+            __syncwarp();
+            dense_tile(in.body, in.halo, in.n_samples, n_vchunks, lutn, out.cand_v, out.cand_capacity, out.tiles, out.counters,
+                       g, s_mask, s_surv, lane);
         }
         __syncwarp();                                    // the masks, the queue and the lists are reused by the next tile
         g = g_next;
@@ -413,20 +449,20 @@ scan2_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, u
 
 }  // namespace
 
-void launch_scan2(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count, cudaStream_t stream) {
+void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs &out, int sm_count, cudaStream_t stream) {
     // occupancy is a property of the device the context lives on
     static int ctas_per_sm[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
     if (!ctas_per_sm[dev]) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan2_kernel, 32, 0) != cudaSuccess || n < 1) n = 16;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, scan_kernel, 32, 0) != cudaSuccess || n < 1) n = 16;
         ctas_per_sm[dev] = n;
     }
-    const uint32_t n_tiles = (uint32_t)((in.n_samples + kHaloSamples + kTile - 1) / kTile);
+    const uint32_t n_tiles = tiles_for(in.n_samples);
     uint32_t grid = (uint32_t)(sm_count * ctas_per_sm[dev]);   // persistent single-warp CTAs, all resident
     if (grid > n_tiles) grid = n_tiles;
-    scan2_kernel<<<grid, 32, 0, stream>>>(in, tab.lutn, out, n_tiles, 1u, 0xffffffffu);
+    scan_kernel<<<grid, 32, 0, stream>>>(in, tab.lutn, out, n_tiles, 1u, 0xffffffffu, 65536u);
 }
 
 }  // namespace modes

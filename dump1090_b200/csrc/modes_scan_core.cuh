@@ -119,5 +119,73 @@ MODES_SCAN_FN uint32_t row_mask(const uint32_t P[kLaneWords + kLookWords], uint3
     return (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
 }
 
+
+// ---- two rows per register --------------------------------------------------------------------
+// The same arithmetic with the two 16-bit halves of a register holding the same sample of two
+// DIFFERENT rows (row A low, row B high) instead of two neighbouring samples of one row: every
+// operand of a position is then a whole register (no odd-aligned copies to build: one PRMT and one
+// bias less per position pair), and the per-step overhead is paid once for 64 positions.
+constexpr int kPairLook = 9;             // registers of the next lane a lane's last positions reach into
+
+// One 32-bit word of each row (two I/Q pairs each) -> X0 = (nA0, nB0), X1 = (nA1, nB1).
+// `c65536` = 65536 as a value the compiler cannot see (keeps the packing on the FMA pipe).
+MODES_SCAN_FN void npack2(uint32_t rawA, uint32_t rawB, uint32_t c65536, uint32_t minus_one, uint32_t &X0, uint32_t &X1) {
+    const uint32_t aA = absdiff127x4(rawA), aB = absdiff127x4(rawB);
+    const uint32_t nA0 = dot4(aA, aA & 0xffffu, 0u), nB0 = dot4(aB, aB & 0xffffu, 0u);
+    const uint32_t ntA = dot4(aA, aA, 0u), ntB = dot4(aB, aB, 0u);
+    const uint32_t x0 = mad(nB0, c65536, nA0);
+    const uint32_t nt = mad(ntB, c65536, ntA);
+    const uint32_t x1 = mad(x0, minus_one, nt);                          // (nA1, nB1) = totals - first samples
+    X0 = min2(x0, kK15); X1 = min2(x1, kK15);
+}
+
+// Weights that put the flags of position k (bit 15 = row A, bit 31 = row B of a masked comparison
+// word) at bits q and 4+q (q = k & 3) of a byte scaled by 128.
+MODES_SCAN_FN constexpr uint32_t pair_weights(int q) { return (1u << (8 + q)) | (1u << (24 + 4 + q)); }
+
+// Positions K0 .. K1-1 of the comparison; accumulates the flags into acc[k / 4].
+template <int K0, int K1>
+MODES_SCAN_FN void rows2_compare(const uint32_t X[32 + kPairLook], uint32_t one, uint32_t minus_one, uint32_t acc[8]) {
+    uint32_t XK[32 + kPairLook];
+#pragma unroll
+    for (int k = K0; k < K1 + kPairLook; k++) XK[k] = mad(X[k], one, kK15);
+#pragma unroll
+    for (int k = K0; k < K1; k++) {
+        const uint32_t AK = min2(XK[k], XK[k + 2]);                        // min(m0, m2) + K
+        const uint32_t B = max2(X[k + 1], X[k + 3]);                       // max(m1, m3)
+        const uint32_t W = max2x3(X[k + 4], X[k + 5], X[k + 6]);           // max(m4, m5, m6)
+        const uint32_t E = max2(X[k + 6], X[k + 8]);                       // max(m6, m8)
+        const uint32_t D1 = mad(B, minus_one, AK);
+        const uint32_t D2 = mad(W, minus_one, XK[k]);
+        const uint32_t D3 = mad(E, minus_one, XK[k + 9]);                  // m9 - max(m6, m8)
+        const uint32_t D4 = mad(X[k + 8], minus_one, XK[k + 7]);           // m7 - m8
+        const uint32_t T = (D1 & D2 & D3) & (D4 & 0x80008000u);
+        acc[k >> 2] = dot4(T, pair_weights(k & 3), acc[k >> 2]);
+    }
+}
+
+// The accumulated flags -> outA / outB: bit p = position p of row A / row B passes.
+MODES_SCAN_FN void rows2_finish(const uint32_t acc[8], uint32_t &outA, uint32_t &outB) {
+    // byte b of m_j = (row B flags of positions 16j+4b..+3) << 4 | (row A flags of the same positions)
+    const uint32_t m0 = (acc[0] >> 7) | (acc[1] << 1) | (acc[2] << 9) | (acc[3] << 17);
+    const uint32_t m1 = (acc[4] >> 7) | (acc[5] << 1) | (acc[6] << 9) | (acc[7] << 17);
+    // nibbles -> two 32-bit masks
+    uint32_t a0 = m0 & 0x0f0f0f0fu, a1 = m1 & 0x0f0f0f0fu, b0 = (m0 >> 4) & 0x0f0f0f0fu, b1 = (m1 >> 4) & 0x0f0f0f0fu;
+    a0 = (a0 | (a0 >> 4)) & 0x00ff00ffu; a1 = (a1 | (a1 >> 4)) & 0x00ff00ffu;
+    b0 = (b0 | (b0 >> 4)) & 0x00ff00ffu; b1 = (b1 | (b1 >> 4)) & 0x00ff00ffu;
+    a0 = (a0 | (a0 >> 8)) & 0xffffu; a1 = (a1 | (a1 >> 8)) & 0xffffu;
+    b0 = (b0 | (b0 >> 8)) & 0xffffu; b1 = (b1 | (b1 >> 8)) & 0xffffu;
+    outA = a0 | (a1 << 16);
+    outB = b0 | (b1 << 16);
+}
+
+// The ten comparisons for positions 0..31 of both rows; X[0..31] = the lane's samples, X[32..40] =
+// the next nine.
+MODES_SCAN_FN void rows2_mask(const uint32_t X[32 + kPairLook], uint32_t one, uint32_t minus_one, uint32_t &outA, uint32_t &outB) {
+    uint32_t acc[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    rows2_compare<0, 32>(X, one, minus_one, acc);
+    rows2_finish(acc, outA, outB);
+}
+
 }  // namespace scan2
 }  // namespace modes

@@ -108,7 +108,7 @@ typedef struct modes_candidate {
  * in stream order; candidates inside a tile are in stream order.  How many positions a tile
  * covers is the scan kernel's business: size tile tables with modes_tile_count(). */
 typedef struct modes_tile { uint32_t offset, count; } modes_tile;
-#define MODES_TILE_SAMPLES 4096             /* tile of the round-1 scan kernel (MODES_SCAN_VARIANT=1) */
+#define MODES_TILE_SAMPLES 7936             /* 8 rows of 31 x 32 positions, see csrc/modes_scan2.cu */
 
 /* Replaces Modes.stat_* (dump1090.c:186-195) in the order the reference prints
  * them (:2994-3003): valid_preamble, out_of_phase, demodulated, goodcrc,

@@ -23,4 +23,22 @@ extern "C" int shim_scan_masks(const uint8_t *iq, uint64_t n_samples, uint64_t n
     return 0;
 }
 
+// Two rows at a time (rows2_mask): row A = positions [0, n_positions), row B starts row_b samples later.
+extern "C" int shim_scan_masks2(const uint8_t *iq, uint64_t n_samples, uint64_t n_positions, uint64_t row_b,
+                                uint32_t *mask_a, uint32_t *mask_b) {
+    using namespace modes::scan2;
+    if (n_positions % 32 || n_samples < row_b + n_positions + 2 * kPairLook + 2) return -1;
+    for (uint64_t p0 = 0; p0 < n_positions; p0 += 32) {
+        uint32_t X[32 + kPairLook + 1];
+        for (int w = 0; w < (32 + kPairLook + 1) / 2; w++) {
+            uint32_t ra, rb;
+            std::memcpy(&ra, iq + 2 * (p0 + 2 * w), 4);
+            std::memcpy(&rb, iq + 2 * (row_b + p0 + 2 * w), 4);
+            npack2(ra, rb, 65536u, 0xffffffffu, X[2 * w], X[2 * w + 1]);
+        }
+        rows2_mask(X, 1u, 0xffffffffu, mask_a[p0 / 32], mask_b[p0 / 32]);
+    }
+    return 0;
+}
+
 extern "C" uint32_t shim_npack(uint32_t raw) { return modes::scan2::npack(raw); }

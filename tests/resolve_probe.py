@@ -17,8 +17,8 @@ cands = C.oracle_scan_candidates(data, fix=0, cap=4_000_000)
 arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE)
 print(f"oracle scan: {len(arr)} candidates in {time.time()-t0:.1f}s", flush=True)
 n_buf = (mib << 20) // (2 * 131072)
-g = (arr["t"] + 2) // 4096
-n_tiles = (n_buf * 131072 + 240 + 4095) // 4096
+g = (arr["t"] + 2) // api.TILE_SAMPLES
+n_tiles = api.tiles_for(n_buf)
 cnt = np.bincount(g, minlength=n_tiles).astype(np.uint32)
 off = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint32)
 tiles = np.zeros(n_tiles, dtype=api.TILE_DTYPE)

@@ -15,8 +15,6 @@ import streams as S
 
 # all three frame-evaluation kernels: thread per candidate (two codings of the per-bit loops) and warp per candidate
 EVAL_VARIANTS = ["serial", "warp", "lean"]
-# both preamble-scan kernels: "2" = modes_scan2.cu (lane = 32 positions), "1" = the round-1 row scan
-SCAN_VARIANTS = ["2", "1"]
 
 
 def _dec_kw(kw):
@@ -90,14 +88,6 @@ def test_candidates_match_oracle(name, aggressive, variant, gpu_decoder_factory,
     candidate with the leaner per-bit loops), incl. the tie-rich streams and the j == 0 retries."""
     monkeypatch.setenv("MODES_EVAL_VARIANT", variant)
     _check_candidates(ALL_STREAMS[name], aggressive, gpu_decoder_factory(aggressive=aggressive))
-
-
-@pytest.mark.parametrize("name", list(ALL_STREAMS))
-@pytest.mark.parametrize("scan", SCAN_VARIANTS)
-def test_scan_variants_match_oracle(name, scan, gpu_decoder_factory, checker_libs, monkeypatch):
-    """Both preamble-scan kernels find exactly the oracle's candidate positions (and records)."""
-    monkeypatch.setenv("MODES_SCAN_VARIANT", scan)
-    _check_candidates(ALL_STREAMS[name], 0, gpu_decoder_factory())
 
 
 @pytest.mark.parametrize("variant", EVAL_VARIANTS)

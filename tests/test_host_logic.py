@@ -151,8 +151,8 @@ def test_parallel_shard_resolve_recovers_from_a_wrong_guess(checker_libs, capfd,
     cands = C.oracle_scan_candidates(data)
     arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE)
 
-    def tiled(sel, n_buffers):                                            # one tile per 4096 positions, like the scan kernel
-        g = (sel["t"] + 2) // 4096
+    def tiled(sel, n_buffers):                                            # one tile per TILE_SAMPLES positions, like the scan kernel
+        g = (sel["t"] + 2) // api.TILE_SAMPLES
         nt = api.tiles_for(n_buffers)
         cnt = np.bincount(g, minlength=nt).astype(np.uint32)
         t = np.zeros(nt, dtype=api.TILE_DTYPE)

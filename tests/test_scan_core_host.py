@@ -20,6 +20,8 @@ def shim():
     lib = ctypes.CDLL(str(SHIM))
     lib.shim_scan_masks.restype = ctypes.c_int
     lib.shim_scan_masks.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+    lib.shim_scan_masks2.restype = ctypes.c_int
+    lib.shim_scan_masks2.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
     lib.shim_npack.restype = ctypes.c_uint32
     lib.shim_npack.argtypes = [ctypes.c_uint32]
     return lib
@@ -62,6 +64,21 @@ def test_row_masks_match_direct_comparisons(shim, name, iq):
     exp = _expected(iq, n_pos)
     assert exp.sum() > 0 or name == "saturated"
     assert np.array_equal(got, exp), f"{np.flatnonzero(got != exp)[:10]}"
+
+
+@pytest.mark.parametrize("name,iq", list(_streams()), ids=[n for n, _ in _streams()])
+def test_two_row_masks_match_direct_comparisons(shim, name, iq):
+    """rows2_mask: the same comparisons with two rows (992 samples apart) sharing the registers."""
+    n_samples = iq.size // 2
+    row_b = 992
+    n_pos = min((n_samples - row_b - 32) // 32 * 32, 32 * 600)
+    a = np.zeros(n_pos // 32, dtype=np.uint32)
+    b = np.zeros(n_pos // 32, dtype=np.uint32)
+    assert shim.shim_scan_masks2(iq.ctypes.data, n_samples, n_pos, row_b, a.ctypes.data, b.ctypes.data) == 0
+    bits = lambda m: ((m[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(bool).ravel()
+    exp = _expected(iq, row_b + n_pos)
+    assert np.array_equal(bits(a), exp[:n_pos])
+    assert np.array_equal(bits(b), exp[row_b: row_b + n_pos])
 
 
 def test_npack_orders_like_the_magnitude_table(shim):
