@@ -20,6 +20,7 @@ BUFFER_BYTES = 262144
 BUFFER_SAMPLES = 131072
 CARRY_BYTES = 476
 TILE_SAMPLES = 7936                       # MODES_TILE_SAMPLES
+ICAO_CACHE_SLOTS = 1024                   # MODES_ICAO_CACHE_SLOTS
 STREAM_EPOCH_MS = 1_000_000_000_000      # MODES_STREAM_EPOCH_MS: start of a file's stream clock for the tracker
 
 EVAL_GATE_OK, EVAL_ERRORS, EVAL_DECODED, EVAL_P2_VALID = 1, 2, 4, 8
@@ -107,7 +108,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_host", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_run_shards", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_format_raw_net", "modes_parse_hex_line", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_get_cache", "modes_resolver_set_cache", "modes_resolver_tail_cache", "modes_resolver_run_tentative", "modes_resolver_commit", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_format_raw_net", "modes_parse_hex_line", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
@@ -182,6 +183,11 @@ def lib():
         L.modes_get_kernel_times.argtypes = [C.c_void_p, C.POINTER(C.c_float * 4)]
         L.modes_launch_count.restype = C.c_uint64
         L.modes_launch_count.argtypes = [C.c_void_p]
+        L.modes_resolver_get_cache.argtypes = [C.c_void_p, C.c_void_p]
+        L.modes_resolver_set_cache.argtypes = [C.c_void_p, C.c_void_p]
+        L.modes_resolver_tail_cache.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_size_t, C.c_void_p]
+        L.modes_resolver_run_tentative.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64]
+        L.modes_resolver_commit.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
         L.modes_tile_count.restype = C.c_size_t
         L.modes_tile_count.argtypes = [C.c_size_t]
         _lib = L
@@ -435,6 +441,35 @@ class Resolver:
         fn = C.cast(None, SINK_FN) if getattr(self, "_native", False) else self._collector.fn
         if lib().modes_resolver_run_shards(self._h, n, cp, tp, nt, bb, fn, None):
             raise RuntimeError("modes_resolver_run_shards failed")
+
+    # ---- one shard of a sharded decode (see include/modes_b200.h and sharded.resolve_distributed)
+    def get_cache(self) -> np.ndarray:
+        out = np.zeros(ICAO_CACHE_SLOTS, dtype=np.uint32)
+        lib().modes_resolver_get_cache(self._h, _ptr(out))
+        return out
+
+    def set_cache(self, cache=None) -> None:
+        c = None if cache is None else np.ascontiguousarray(cache, dtype=np.uint32)
+        lib().modes_resolver_set_cache(self._h, None if c is None else _ptr(c))
+
+    def tail_cache(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0, n_tail_tiles: int | None = None) -> np.ndarray:
+        out = np.zeros(ICAO_CACHE_SLOTS, dtype=np.uint32)
+        if n_tail_tiles is None:
+            n_tail_tiles = max(tiles.size // 16, 128)
+        if lib().modes_resolver_tail_cache(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base, n_tail_tiles, _ptr(out)):
+            raise RuntimeError("modes_resolver_tail_cache failed")
+        return out
+
+    def run_tentative(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0) -> None:
+        self._held = (cands, tiles)                       # the records must outlive the commit
+        if lib().modes_resolver_run_tentative(self._h, _ptr(cands), _ptr(tiles), tiles.size, buffer_base):
+            raise RuntimeError("modes_resolver_run_tentative failed")
+
+    def commit(self) -> None:
+        fn = C.cast(None, SINK_FN) if getattr(self, "_native", False) else self._collector.fn
+        if lib().modes_resolver_commit(self._h, fn, None):
+            raise RuntimeError("modes_resolver_commit without a tentative run")
+        self._held = None
 
     def take_messages(self):
         out, self._collector.messages = self._collector.messages, []

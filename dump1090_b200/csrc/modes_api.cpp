@@ -532,7 +532,11 @@ int modes_resolve(modes_ctx *ctx, const modes_candidate *candidates, const modes
     return 0;
 }
 
-struct modes_resolver { ResolveState rs; ResolveConfig rc; MessageOut out; ResolveScratch *scratch = nullptr; };
+struct modes_resolver {
+    ResolveState rs; ResolveConfig rc; MessageOut out; ResolveScratch *scratch = nullptr;
+    ResolveState tentative;             // end state of the last modes_resolver_run_tentative
+    bool has_tentative = false;
+};
 
 modes_resolver *modes_resolver_create(const modes_config *cfg) {
     modes_resolver *r = new (std::nothrow) modes_resolver();
@@ -562,6 +566,56 @@ int modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_ca
     if (!r || (n_shards && (!candidates || !tiles || !n_tiles || !buffer_base))) return -1;
     r->out.sink = sink; r->out.user = user;
     resolve_shards(r->rs, r->rc, n_shards, candidates, tiles, n_tiles, buffer_base, r->out, r->scratch);
+    return 0;
+}
+
+int modes_resolver_get_cache(const modes_resolver *r, uint32_t cache[MODES_ICAO_CACHE_SLOTS]) {
+    if (!r || !cache) return -1;
+    memcpy(cache, r->has_tentative ? r->tentative.icao : r->rs.icao, sizeof(r->rs.icao));
+    return 0;
+}
+
+int modes_resolver_set_cache(modes_resolver *r, const uint32_t cache[MODES_ICAO_CACHE_SLOTS]) {
+    if (!r) return -1;
+    if (cache) memcpy(r->rs.icao, cache, sizeof(r->rs.icao)); else memset(r->rs.icao, 0, sizeof(r->rs.icao));
+    r->rs.cur_buffer = -1; r->rs.next_j = 0;
+    r->has_tentative = false;
+    return 0;
+}
+
+int modes_resolver_tail_cache(const modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                              size_t n_tiles, int64_t buffer_base, size_t n_tail_tiles, uint32_t cache[MODES_ICAO_CACHE_SLOTS]) {
+    if (!r || !tiles || !cache) return -1;
+    ResolveState st;
+    st.reset();
+    ResolveScratch *tmp = scratch_create();
+    if (!tmp) return -1;
+    if (n_tail_tiles > n_tiles) n_tail_tiles = n_tiles;
+    resolve_tentative(st, r->rc, candidates, tiles + (n_tiles - n_tail_tiles), n_tail_tiles, buffer_base, tmp);
+    scratch_destroy(tmp);
+    memcpy(cache, st.icao, sizeof(st.icao));
+    return 0;
+}
+
+int modes_resolver_run_tentative(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                                 size_t n_tiles, int64_t buffer_base) {
+    if (!r || !tiles) return -1;
+    r->tentative = r->rs;
+    memset(r->tentative.stats, 0, sizeof(r->tentative.stats));
+    r->tentative.cur_buffer = -1; r->tentative.next_j = 0;
+    resolve_tentative(r->tentative, r->rc, candidates, tiles, n_tiles, buffer_base, r->scratch);
+    r->has_tentative = true;
+    return 0;
+}
+
+int modes_resolver_commit(modes_resolver *r, modes_sink_fn sink, void *user) {
+    if (!r || !r->has_tentative) return -1;
+    r->out.sink = sink; r->out.user = user;
+    for (int i = 0; i < 8; i++) r->rs.stats[i] += r->tentative.stats[i];
+    memcpy(r->rs.icao, r->tentative.icao, sizeof(r->rs.icao));
+    r->rs.cur_buffer = r->tentative.cur_buffer; r->rs.next_j = r->tentative.next_j;
+    resolve_commit(r->out, r->scratch);
+    r->has_tentative = false;
     return 0;
 }
 

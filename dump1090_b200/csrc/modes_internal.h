@@ -103,6 +103,11 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
 void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
                     const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
                     MessageOut &out, ResolveScratch *scratch);
+// A shard resolved from a GUESSED address cache (one rank / one GPU thread of a sharded decode):
+// verdicts only, deliveries held back in the scratch until the guess is verified.
+void resolve_tentative(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
+                       size_t n_tiles, int64_t buffer_base, ResolveScratch *scratch);
+void resolve_commit(MessageOut &out, ResolveScratch *scratch);
 // The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
 int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
 

@@ -362,6 +362,17 @@ void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_
                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
 }
 
+void resolve_tentative(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
+                       size_t n_tiles, int64_t buffer_base, ResolveScratch *scratch) {
+    scratch->deliveries.clear();
+    judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, scratch->deliveries);
+}
+
+void resolve_commit(MessageOut &out, ResolveScratch *scratch) {
+    deliver(scratch->deliveries, out);
+    scratch->deliveries.clear();
+}
+
 // Several shards of one stream (e.g. one per GPU), resolved concurrently and exactly.
 //
 // The only state that crosses a shard boundary is the ICAO address cache (skip state restarts at

@@ -101,6 +101,61 @@ def resolve_gathered(resolver, gathered, plan) -> None:
     resolver.run_shards(shards)
 
 
+def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_base: int, dist=None, group=None,
+                        start_cache=None) -> dict:
+    """Every rank resolves ITS OWN shard (records in its own host memory) and the result is exactly
+    the sequential one: no rank sees another rank's records, only 4 KiB address caches travel.
+
+    Protocol (include/modes_b200.h, "one shard of a sharded decode"): all-gather what the tail of
+    each shard leaves in an empty cache; rank k guesses its starting cache as the job's starting
+    cache overwritten by shard k-1's tail; every rank resolves tentatively; all-gather (guess, end
+    cache); a rank is verified when its guess equals what the previous rank really ended with and
+    that rank is verified; unverified ranks run again from the now known cache.  One round is the
+    rule, world rounds the worst case.  Then every rank commits (delivers) its own messages.
+    `group` must accept CPU tensors (gloo).  Returns {"rounds", "end_cache" (of the whole job)}."""
+    import torch
+    world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size(group)
+    rank = 0 if world == 1 else dist.get_rank(group)
+    S0 = np.zeros(api.ICAO_CACHE_SLOTS, dtype=np.uint32) if start_cache is None else np.asarray(start_cache, dtype=np.uint32)
+    cands = np.ascontiguousarray(cands)
+    tiles = np.ascontiguousarray(tiles)
+
+    def all_gather(vec: np.ndarray) -> np.ndarray:
+        if world == 1:
+            return vec[None, :]
+        t = torch.from_numpy(vec.astype(np.int64))            # gloo has no uint32
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t, group=group)
+        return np.stack([o.numpy().astype(np.uint32) for o in outs])
+
+    tails = all_gather(resolver.tail_cache(cands, tiles, buffer_base)) if world > 1 else None
+    guess = S0.copy()
+    if rank > 0:
+        t = tails[rank - 1]
+        guess[t != 0] = t[t != 0]
+    rounds, need_run, end = 0, True, None
+    while True:
+        if need_run:
+            resolver.set_cache(guess)
+            resolver.run_tentative(cands, tiles, buffer_base)
+            end = resolver.get_cache()
+        rounds += 1
+        both = all_gather(np.concatenate([guess, end]))
+        G, E = both[:, : api.ICAO_CACHE_SLOTS], both[:, api.ICAO_CACHE_SLOTS:]
+        ok = [bool(np.array_equal(G[0], S0))]
+        for k in range(1, world):
+            ok.append(ok[k - 1] and bool(np.array_equal(G[k], E[k - 1])))
+        if all(ok):
+            break
+        # everything up to the first unverified rank is final; from there on, run again from the
+        # cache the predecessor ended with in this round (right for the first of them at least)
+        need_run = not ok[rank]
+        if need_run:
+            guess = E[rank - 1].copy() if rank > 0 else S0.copy()
+    resolver.commit()
+    return {"rounds": rounds, "end_cache": E[world - 1].copy()}
+
+
 def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):
     """Gather fixed-size record/tile buffers to rank `dst` with no host round trip (counts travel
     in the tile tables).  `out` = preallocated ([world x cands], [world x tiles]) on dst.  Returns

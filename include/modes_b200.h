@@ -191,6 +191,23 @@ int  modes_resolver_run(modes_resolver *r, const modes_candidate *candidates, co
 int  modes_resolver_run_shards(modes_resolver *r, size_t n_shards, const modes_candidate *const *candidates,
                                const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
                                modes_sink_fn sink, void *user);
+/* One shard of a sharded decode, resolved where its records are (one rank or GPU thread per shard).
+ * The only state crossing a shard boundary is the 1024-slot address cache (dump1090.c:335, :898-983):
+ * a shard is resolved TENTATIVELY from a guess of the cache at its start — the job's starting cache
+ * overwritten by what the tail of the previous shard leaves (modes_resolver_tail_cache, exchanged
+ * between the shards' owners, 4 KiB) — the guess is compared with what the previous shard really
+ * ended with (modes_resolver_get_cache after its tentative run), and a shard whose guess was wrong
+ * is run again from the right cache.  modes_resolver_commit then delivers the messages and adds the
+ * statistics.  dump1090_b200/sharded.py:resolve_distributed is the protocol over torch.distributed;
+ * modes_resolver_run_shards is the same thing inside one process. */
+#define MODES_ICAO_CACHE_SLOTS 1024
+int  modes_resolver_get_cache(const modes_resolver *r, uint32_t cache[MODES_ICAO_CACHE_SLOTS]);  /* of the tentative run if one is pending */
+int  modes_resolver_set_cache(modes_resolver *r, const uint32_t cache[MODES_ICAO_CACHE_SLOTS]);  /* NULL = empty; drops a pending run */
+int  modes_resolver_tail_cache(const modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                               size_t n_tiles, int64_t buffer_base, size_t n_tail_tiles, uint32_t cache[MODES_ICAO_CACHE_SLOTS]);
+int  modes_resolver_run_tentative(modes_resolver *r, const modes_candidate *candidates, const modes_tile *tiles,
+                                  size_t n_tiles, int64_t buffer_base);            /* records must stay valid until commit */
+int  modes_resolver_commit(modes_resolver *r, modes_sink_fn sink, void *user);
 int  modes_resolver_reset(modes_resolver *r);           /* forget ICAO cache, skip state, statistics */
 int  modes_resolver_stats(const modes_resolver *r, modes_stats *out);
 int    modes_resolver_set_output(modes_resolver *r, modes_message *out, size_t capacity);   /* like modes_set_output */
