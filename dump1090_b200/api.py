@@ -385,6 +385,14 @@ class Decoder:
         self._check(lib().modes_detect_fetch(self._h, _ptr(cands), _ptr(tiles)))
         return cands[:n], tiles
 
+    def detect_fetch_into(self, cands: np.ndarray, tiles: np.ndarray):
+        """Like detect_fetch, into caller-owned arrays (pinned memory for full PCIe speed); returns views."""
+        n = self.detect_wait()
+        if n > cands.size:
+            raise RuntimeError(f"record buffer too small: {n} > {cands.size}")
+        self._check(lib().modes_detect_fetch(self._h, _ptr(cands), _ptr(tiles)))
+        return cands[:n], tiles
+
     def resolve(self, cands: np.ndarray, tiles: np.ndarray, buffer_base: int = 0) -> None:
         self._check(lib().modes_resolve(self._h, _ptr(np.ascontiguousarray(cands)), _ptr(np.ascontiguousarray(tiles)),
                                         tiles.size, buffer_base))

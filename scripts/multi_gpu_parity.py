@@ -8,6 +8,7 @@ from dump1090_b200 import api, sharded, synth
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+host_group = dist.new_group(backend="gloo")
 ok_all = True
 for seed, nsamples, kw in [(41, 131072 * 7 + 5000, {}), (42, 131072 * 4, dict(aggressive=1)), (43, 131072 * 9 + 77, dict(fix_errors=0))]:
     data = synth.random_traffic(nsamples, nsamples // 600, seed)
@@ -41,6 +42,18 @@ for seed, nsamples, kw in [(41, 131072 * 7 + 5000, {}), (42, 131072 * 4, dict(ag
         res2 = api.Resolver(**kw); res2.set_output_array(200000)
         res2.run_shards([(c, (t if plan[r][1] else t[:0]), plan[r][0]) for r, (c, t) in enumerate(fused)])
         lines2 = [res2._out[i].raw_line() for i in range(res2.output_count())]
+    # the same job with no record gather at all: every rank fetches its own records over its own
+    # PCIe link and resolves its own shard (only 4 KiB address caches travel); what bench.py times
+    res3 = api.Resolver(**kw); res3.set_output_array(200000)
+    if count:
+        dec.detect_device(shard.data_ptr(), count, sharded.carry_before(padded, first))
+        c3, t3 = dec.detect_fetch(count)
+    else:
+        c3, t3 = np.zeros(0, dtype=api.CANDIDATE_DTYPE), np.zeros(0, dtype=api.TILE_DTYPE)
+    info = sharded.resolve_distributed(res3, c3, t3, first, dist, host_group)
+    mine = ([res3._out[i].raw_line() for i in range(res3.output_count())], list(res3.stats().values()), info["rounds"])
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0, group=host_group)
     if rank == 0:
         res = api.Resolver(**kw); res.set_output_array(200000)
         sharded.resolve_gathered(res, g, plan)
@@ -49,8 +62,11 @@ for seed, nsamples, kw in [(41, 131072 * 7 + 5000, {}), (42, 131072 * 4, dict(ag
         exp, st = C.oracle_decode(data, **okw)
         ok = lines == [m.hexline() for m in exp] and list(res.stats().values()) == st
         ok = ok and lines2 == lines and res2.stats() == res.stats()
+        lines3 = [l for part in parts for l in part[0]]
+        stats3 = [sum(part[1][i] for part in parts) for i in range(8)]
+        ok = ok and lines3 == lines and stats3 == st
         ok_all &= ok
-        print(f"world={world} seed={seed} buffers={nbuf_total} msgs={len(lines)} parity={'OK' if ok else 'MISMATCH'}", flush=True)
+        print(f"world={world} seed={seed} buffers={nbuf_total} msgs={len(lines)} rounds={max(p[2] for p in parts)} parity={'OK' if ok else 'MISMATCH'}", flush=True)
     dist.barrier(); pg.close()
     dec.close()
 dist.barrier()
