@@ -481,7 +481,7 @@ def run_ours(args) -> None:
         dec.detect_device(d_iq.data_ptr(), bbuf, carry0)
         cands, tiles = dec.detect_fetch(bbuf)
         seq = api.Resolver(**cfg)
-        seq_out = seq.set_output_array(msg_cap)
+        seq_out = seq.set_output_array(msg_cap * (world if rank == 0 else 1))
         ok_seq = None
         if world == 1 and nbatch == 1:
             seq.run(cands, tiles, 0)

@@ -500,13 +500,29 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
     const uint32_t total_warps = gridDim.x * kSerWarps;
     const uint32_t *body32 = reinterpret_cast<const uint32_t *>(in.body);
 
+    // Chunks of 32 candidates are handed out from a global counter, requested TWO chunks ahead: one
+    // chunk ahead the candidate positions are already loaded, and while the current chunk is
+    // evaluated the next chunk's windows are on their way into L2 (one prefetch per 128-byte line).
+    // (The counter values are used untouched until a chunk later: arithmetic on them right away
+    // would wait for the atomic's round trip.)
     uint32_t chunk = blockIdx.x * kSerWarps + warp;
+    uint32_t next1 = 0, ahead_raw = 0;
+    if (lane == 0) next1 = atomicAdd(&counters[3], 1u);
+    next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
+    uint32_t my_v = 0;
+    if (chunk < n_chunks) {
+        const uint32_t n0 = n_cand - chunk * 32 < 32u ? n_cand - chunk * 32 : 32u;
+        my_v = cand_v[chunk * 32 + ((uint32_t)lane < n0 ? lane : n0 - 1)];
+    }
     while (chunk < n_chunks) {
-        uint32_t next = 0;
-        if (lane == 0) next = total_warps + atomicAdd(&counters[3], 1u);
+        if (lane == 0) ahead_raw = atomicAdd(&counters[3], 1u);
         const uint32_t base = chunk * 32;
-        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;
-        const uint32_t my_v = cand_v[base + ((uint32_t)lane < n ? lane : n - 1)];   // idle lanes of the last chunk duplicate its last candidate
+        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;   // idle lanes of the last chunk duplicate its last candidate
+        uint32_t v_next = 0;
+        if (next1 < n_chunks) {
+            const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
+            v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
+        }
 
         // stage the windows: row c = candidate c, words (first>>1) .. +120 of the body
         if (__all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples)) {
@@ -536,6 +552,14 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
             }
         }
         __syncwarp();
+        // the next chunk's windows -> L2 (484 bytes from a 4-byte aligned address: five 128-byte lines)
+        if (v_next > (uint32_t)kHaloSamples) {
+            const uint8_t *wp = in.body + 4ull * ((v_next - 1 - kHaloSamples) >> 1);
+            if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
+            }
+        }
 
         uint32_t rec[14];
         if ((uint32_t)lane < n) {
@@ -554,7 +578,9 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
         uint32_t *dst = reinterpret_cast<uint32_t *>(records + base);
         for (uint32_t i = lane; i < n * 14; i += 32) dst[i] = wwin[i];
         __syncwarp();
-        chunk = __shfl_sync(0xffffffffu, next, 0);
+        chunk = next1;
+        my_v = v_next;
+        next1 = total_warps + __shfl_sync(0xffffffffu, ahead_raw, 0);
     }
 }
 
