@@ -519,10 +519,6 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
         const uint32_t base = chunk * 32;
         const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;   // idle lanes of the last chunk duplicate its last candidate
         uint32_t v_next = 0;
-        if (next1 < n_chunks) {
-            const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
-            v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
-        }
 
         // stage the windows: row c = candidate c, words (first>>1) .. +120 of the body
         if (__all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples)) {
@@ -536,8 +532,16 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
                 cp_async4(dst, wp); cp_async4(dst + 128u, wp + 32); cp_async4(dst + 256u, wp + 64);
                 if (lane < serial::kWindowWords - 96) cp_async4(dst + 384u, wp + 96);
             }
+            if (next1 < n_chunks) {                        // the next chunk's positions: loaded behind the copies, used a chunk later
+                const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
+                v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
+            }
             asm volatile("cp.async.wait_all;" ::: "memory");
         } else {
+            if (next1 < n_chunks) {
+                const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
+                v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
+            }
             for (uint32_t c = 0; c < n; c++) {
                 const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
                 uint32_t *row = wwin + c * kSerRow;

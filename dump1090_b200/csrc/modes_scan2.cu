@@ -398,20 +398,31 @@ scan_kernel(BatchView in, const uint16_t *__restrict__ lutn, ScanOutputs out, ui
                         raw[k][4] = __ldg(p + 4); raw[k][5] = __ldg(p + 5); raw[k][6] = __ldg(p + 11);
                         raw[k][7] = __ldg(p + 12); raw[k][8] = __ldg(p + 13); raw[k][9] = __ldg(p + 14);
                     }
+                    // Most survivors are noise and fail by a wide margin; those are decided on the squared
+                    // magnitudes alone and skip the table (their lanes make no memory requests):
+                    //   m = round(360 sqrt(n))  =>  6(mx+1) >= 2160 sqrt(nx) + 3  and
+                    //   m0+m2+m7+m9 <= 360 (sqrt n0 + sqrt n2 + sqrt n7 + sqrt n9) + 2 <= 720 sqrt(n0+n2+n7+n9) + 2,
+                    // so 9 nx >= n0+n2+n7+n9 implies 6(mx+1) > m0+m2+m7+m9: the test of dump1090.c:1624-1642 fails.
                     uint32_t m[kExactRounds][5];
+                    bool undecided[kExactRounds];
 #pragma unroll
                     for (int k = 0; k < kExactRounds; k++) {
                         uint32_t n[10];
 #pragma unroll
                         for (int j = 0; j < 10; j++) n[j] = n_of(raw[k][j]);
                         const uint32_t nx = max(max(max(n[4], n[5]), max(n[6], n[7])), max(n[8], n[9]));
+                        undecided[k] = 9u * nx < n[0] + n[1] + n[2] + n[3];
 #pragma unroll
-                        for (int j = 0; j < 4; j++) m[k][j] = __ldg(lutn + n[j]);
-                        m[k][4] = __ldg(lutn + nx);
+                        for (int j = 0; j < 5; j++) m[k][j] = 0u;
+                        if (undecided[k]) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++) m[k][j] = __ldg(lutn + n[j]);
+                            m[k][4] = __ldg(lutn + nx);
+                        }
                     }
 #pragma unroll
                     for (int k = 0; k < kExactRounds; k++)                // dump1090.c:1624-1642, see high_rule
-                        pass[k] = 6 * ((int)m[k][4] + 1) <= (int)(m[k][0] + m[k][1] + m[k][2] + m[k][3]);
+                        pass[k] = undecided[k] && 6 * ((int)m[k][4] + 1) <= (int)(m[k][0] + m[k][1] + m[k][2] + m[k][3]);
                 } else {
 #pragma unroll
                     for (int k = 0; k < kExactRounds; k++)
