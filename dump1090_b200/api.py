@@ -29,7 +29,7 @@ EVAL_GATE_OK, EVAL_ERRORS, EVAL_DECODED, EVAL_P2_VALID = 1, 2, 4, 8
 class Config(C.Structure):
     _fields_ = [("fix_errors", C.c_int32), ("aggressive", C.c_int32), ("check_crc", C.c_int32),
                 ("drop_eof_buffer", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32),
-                ("max_batch_bytes", C.c_uint64)]
+                ("max_batch_bytes", C.c_uint64), ("n_gpus", C.c_int32), ("reserved", C.c_int32)]
 
 
 _MSG_A = ("errorbit aa1 aa2 aa3 phase_corrected ca iid metype mesub heading_is_valid heading "
@@ -108,7 +108,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_sink", "modes_process", "modes_finish", "modes_reset", "modes_get_stats",
            "modes_compute_magnitude", "modes_detect_device", "modes_detect_host", "modes_detect_wait", "modes_detect_fetch",
            "modes_resolve", "modes_resolver_create", "modes_resolver_destroy", "modes_resolver_run",
-           "modes_resolver_run_shards", "modes_resolver_get_cache", "modes_resolver_set_cache", "modes_resolver_tail_cache", "modes_resolver_run_tentative", "modes_resolver_commit", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_format_message", "modes_format_raw_net", "modes_parse_hex_line", "modes_stream", "modes_set_stream",
+           "modes_resolver_run_shards", "modes_resolver_get_cache", "modes_resolver_set_cache", "modes_resolver_tail_cache", "modes_resolver_run_tentative", "modes_resolver_commit", "modes_resolver_reset", "modes_resolver_stats", "modes_resolver_set_output", "modes_resolver_output_count", "modes_decode_frame", "modes_decode_frames", "modes_format_message", "modes_format_raw_net", "modes_parse_hex_line", "modes_stream", "modes_set_stream",
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
@@ -204,13 +204,14 @@ def parse_hex_line(line: str | bytes):
 
 
 def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, device=0, profile=0,
-                max_batch_bytes=0) -> Config:
+                max_batch_bytes=0, n_gpus=0) -> Config:
     cfg = Config()
     lib().modes_default_config(C.byref(cfg))
     cfg.fix_errors, cfg.aggressive, cfg.check_crc = int(fix_errors), int(aggressive), int(check_crc)
     cfg.drop_eof_buffer, cfg.device, cfg.profile = int(drop_eof_buffer), int(device), int(profile)
     if max_batch_bytes:
         cfg.max_batch_bytes = int(max_batch_bytes)
+    cfg.n_gpus = int(n_gpus)
     return cfg
 
 
@@ -402,6 +403,14 @@ class Decoder:
         m = Message()
         self._check(lib().modes_decode_frame(self._h, buf, C.byref(m)))
         return m
+
+    def decode_frames(self, frames) -> list:
+        """A batch of frames (each padded to 14 bytes) through the hex door in one launch."""
+        n = len(frames)
+        buf = (C.c_uint8 * (14 * n))(*[b for f in frames for b in (list(f) + [0] * (14 - len(f)))])
+        out = (Message * n)()
+        self._check(lib().modes_decode_frames(self._h, buf, n, out))
+        return [out[i] for i in range(n)]
 
     def publish_count(self, dst_ptr: int) -> None:
         self._check(lib().modes_detect_publish_count(self._h, C.c_void_p(dst_ptr)))

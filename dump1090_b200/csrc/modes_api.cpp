@@ -63,6 +63,12 @@ struct modes_ctx {
     DeviceTables tab{};
     Slot slot[2];
     Slot detect;                      // stage-level API workspace
+    // cfg.n_gpus > 1: this context is the front of a multi-GPU decode and owns one single-GPU
+    // context per device; it keeps the stream state, the resolve state and the outputs itself
+    // hex door staging (modes_decode_frames)
+    uint8_t *d_frames = nullptr; modes_frame_eval *d_frame_evals = nullptr, *h_frame_evals = nullptr; size_t frames_cap = 0;
+    std::vector<modes_ctx *> gpus;
+    size_t group_n[2] = {0, 0};       // batches in flight per slot parity
     uint64_t last_detect_count = 0;
     // stream state
     uint8_t *pending = nullptr;       // pinned, one reference buffer
@@ -279,8 +285,75 @@ int collect(modes_ctx *ctx, Slot &s) {
     return 0;
 }
 
+// Multi-GPU: wait for the group of batches in slot `parity` (one per GPU), bring their records to
+// the host over every GPU's own link at once, and resolve the group exactly, shards in parallel.
+int collect_group(modes_ctx *ctx, int parity) {
+    const size_t n = ctx->group_n[parity];
+    if (!n) return 0;
+    ctx->group_n[parity] = 0;
+    std::vector<const modes_candidate *> cands(n);
+    std::vector<const modes_tile *> tiles(n);
+    std::vector<size_t> n_tiles(n);
+    std::vector<int64_t> base(n);
+    for (size_t k = 0; k < n; k++) {
+        modes_ctx *g = ctx->gpus[k];
+        Slot &s = g->slot[parity];
+        CK(ctx, cudaSetDevice(g->cfg.device));
+        uint64_t nc = 0;
+        s.busy = false;
+        if (wait_batch(g, s, &nc)) return fail(ctx, "GPU %d: %s", g->cfg.device, g->err.c_str());
+        s.busy = false;
+        n_tiles[k] = tiles_for((uint64_t)s.n_buffers * kBufSamples);
+        if (host_ensure(g, s, nc, n_tiles[k])) return fail(ctx, "GPU %d: %s", g->cfg.device, g->err.c_str());
+        if (nc) CK(ctx, cudaMemcpyAsync(s.h_records, s.out_records, nc * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.h_tiles, s.out_tiles, n_tiles[k] * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
+        cands[k] = s.h_records; tiles[k] = s.h_tiles; base[k] = s.buffer_base;
+    }
+    for (size_t k = 0; k < n; k++) {
+        CK(ctx, cudaSetDevice(ctx->gpus[k]->cfg.device));
+        CK(ctx, cudaStreamSynchronize(ctx->gpus[k]->slot[parity].stream));
+    }
+    ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
+    resolve_shards(ctx->rs, rc, n, cands.data(), tiles.data(), n_tiles.data(), base.data(), ctx->out, ctx->scratch);
+    return 0;
+}
+
+// Multi-GPU streaming decode: batches of whole buffers dealt round-robin to the GPUs, one group of
+// gpus.size() batches in flight per slot parity; group g-1 is resolved while group g uploads and runs.
+int run_buffers_multi(modes_ctx *ctx, const uint8_t *host_iq, size_t n_buffers) {
+    size_t max_b = (size_t)(ctx->cfg.max_batch_bytes / MODES_BUFFER_BYTES);
+    if (max_b < 1) max_b = 1;
+    int cur = 0;
+    bool have_prev = false;
+    while (n_buffers) {
+        size_t k = 0;
+        for (; k < ctx->gpus.size() && n_buffers; k++) {
+            // an even share of what is left, so that a short call still uses every GPU
+            size_t nb = (n_buffers + (ctx->gpus.size() - k) - 1) / (ctx->gpus.size() - k);
+            if (nb > max_b) nb = max_b;
+            modes_ctx *g = ctx->gpus[k];
+            Slot &s = g->slot[cur];
+            CK(ctx, cudaSetDevice(g->cfg.device));
+            s.buffer_base = ctx->buffers_done;
+            if (submit(g, s, host_iq, nullptr, nb, ctx->carry, nullptr, 0, nullptr)) return fail(ctx, "GPU %d: %s", g->cfg.device, g->err.c_str());
+            memcpy(ctx->carry, host_iq + nb * MODES_BUFFER_BYTES - MODES_CARRY_BYTES, MODES_CARRY_BYTES);
+            ctx->buffers_done += (int64_t)nb;
+            host_iq += nb * MODES_BUFFER_BYTES;
+            n_buffers -= nb;
+            ctx->launches += 2;
+        }
+        ctx->group_n[cur] = k;
+        if (have_prev && collect_group(ctx, cur ^ 1)) return -1;
+        have_prev = true;
+        cur ^= 1;
+    }
+    if (collect_group(ctx, cur ^ 1)) return -1;
+    return cudaSetDevice(ctx->cfg.device) == cudaSuccess ? 0 : fail(ctx, "cudaSetDevice failed");
+}
+
 // Decode n_buffers whole reference buffers that sit in host memory.
 int run_buffers(modes_ctx *ctx, const uint8_t *host_iq, size_t n_buffers) {
+    if (!ctx->gpus.empty()) return run_buffers_multi(ctx, host_iq, n_buffers);
     size_t max_b = (size_t)(ctx->cfg.max_batch_bytes / MODES_BUFFER_BYTES);
     if (max_b < 1) max_b = 1;
     int cur = 0;
@@ -323,16 +396,20 @@ void modes_default_config(modes_config *cfg) {
     cfg->device = 0;
     cfg->profile = 0;
     cfg->max_batch_bytes = 64ull << 20;
+    cfg->n_gpus = 1;
 }
 
 const char *modes_last_error(const modes_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 void modes_destroy(modes_ctx *ctx) {
     if (!ctx) return;
+    for (modes_ctx *g : ctx->gpus) modes_destroy(g);
+    ctx->gpus.clear();
     cudaSetDevice(ctx->cfg.device);
     if (ctx->own_detect_stream) { cudaStreamSynchronize(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
     cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
+    cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
     if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
     scratch_destroy(ctx->scratch);
@@ -384,6 +461,20 @@ modes_ctx *modes_create(const modes_config *cfg) {
     ctx->rs.reset();
     memset(ctx->carry, 127, sizeof(ctx->carry));
     if (create_impl(ctx)) { modes_destroy(ctx); return nullptr; }
+    if (ctx->cfg.n_gpus > 1) {
+        int ndev = 0;
+        cudaGetDeviceCount(&ndev);
+        for (int k = 0; k < ctx->cfg.n_gpus; k++) {
+            modes_config c = ctx->cfg;
+            c.n_gpus = 1;
+            c.profile = 0;
+            c.device = (ctx->cfg.device + k) % (ndev > 0 ? ndev : 1);   // fewer devices than shards: reuse them round-robin
+            modes_ctx *g = modes_create(&c);
+            if (!g) { modes_destroy(ctx); return nullptr; }               // g_create_error holds the reason
+            ctx->gpus.push_back(g);
+        }
+        cudaSetDevice(ctx->cfg.device);
+    }
     return ctx;
 }
 
@@ -641,23 +732,37 @@ int modes_resolver_stats(const modes_resolver *r, modes_stats *out) {
     return 0;
 }
 
-int modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out) {
-    if (!ctx || !msg || !out) return -1;
+int modes_decode_frames(modes_ctx *ctx, const uint8_t *frames, size_t n, modes_message *out) {
+    if (!ctx || (n && (!frames || !out))) return -1;
+    if (!n) return 0;
+    if (n > 0x7fffffffu) return fail(ctx, "too many frames");
     CK(ctx, cudaSetDevice(ctx->cfg.device));
-    uint8_t *d_in = nullptr; modes_frame_eval *d_out = nullptr; modes_frame_eval h;
+    // persistent device / pinned staging, grown on demand (the hex door is called per line by a
+    // network feeder: no allocation per call)
+    if (ctx->frames_cap < n) {
+        cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
+        ctx->d_frames = nullptr; ctx->d_frame_evals = nullptr; ctx->h_frame_evals = nullptr; ctx->frames_cap = 0;
+        const size_t cap = n < 64 ? 64 : n + n / 2;
+        CK(ctx, cudaMalloc(&ctx->d_frames, cap * 14));
+        CK(ctx, cudaMalloc(&ctx->d_frame_evals, cap * sizeof(modes_frame_eval)));
+        CK(ctx, cudaMallocHost(&ctx->h_frame_evals, cap * sizeof(modes_frame_eval)));
+        ctx->frames_cap = cap;
+    }
     cudaStream_t st = ctx->detect.stream;
-    CK(ctx, cudaMalloc(&d_in, 16));
-    if (cudaMalloc(&d_out, sizeof(h)) != cudaSuccess) { cudaFree(d_in); return fail(ctx, "cudaMalloc failed"); }
-    cudaMemcpyAsync(d_in, msg, 14, cudaMemcpyHostToDevice, st);
-    launch_eval_frames(d_in, d_out, 1, ctx->tab, ctx->cfg.fix_errors, ctx->cfg.aggressive, st);
+    CK(ctx, cudaMemcpyAsync(ctx->d_frames, frames, n * 14, cudaMemcpyHostToDevice, st));
+    launch_eval_frames(ctx->d_frames, ctx->d_frame_evals, (uint32_t)n, ctx->tab, ctx->cfg.fix_errors, ctx->cfg.aggressive, st);
     ctx->launches++;
-    cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(d_in); cudaFree(d_out);
-    if (e != cudaSuccess) return fail(ctx, "frame kernel failed: %s", cudaGetErrorString(e));
-    finish_message(ctx->rs, h, out);
-    out->sample_pos = -1;
+    CK(ctx, cudaMemcpyAsync(ctx->h_frame_evals, ctx->d_frame_evals, n * sizeof(modes_frame_eval), cudaMemcpyDeviceToHost, st));
+    CK(ctx, cudaStreamSynchronize(st));
+    for (size_t i = 0; i < n; i++) {                       // in order: the address cache is sequential
+        finish_message(ctx->rs, ctx->h_frame_evals[i], &out[i]);
+        out[i].sample_pos = -1;
+    }
     return 0;
+}
+
+int modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out) {
+    return modes_decode_frames(ctx, msg, 1, out);
 }
 
 void *modes_stream(modes_ctx *ctx) { return ctx ? (void *)ctx->detect.stream : nullptr; }

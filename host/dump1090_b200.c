@@ -6,7 +6,8 @@
  * Supported options (same spelling and meaning as the reference):
  *   --ifile <file>  --raw  --onlyaddr  --no-fix  --no-crc-check  --aggressive  --stats
  * Additions: --drop-eof-buffer (reproduce the stock binary's usual EOF race
- * outcome), --device <n>, --chunk <bytes> (read size); --sbs prints the SBS (BaseStation)
+ * outcome), --device <n>, --gpus <n> (deal the buffers to n GPUs starting at --device, one copy
+ * stream per GPU), --chunk <bytes> (read size); --sbs prints the SBS (BaseStation)
  * line of every message instead (what the reference writes to port 30003, dump1090.c:2396) and
  * --aircraft-json prints the tracked aircraft as the reference's /data.json at the end (:2505),
  * both with stream time (MODES_STREAM_EPOCH_MS + sample position / 2 MHz) as the clock.
@@ -68,6 +69,7 @@ int main(int argc, char **argv) {
         else if (!strcmp(argv[j], "--sbs")) opt_sbs = 1;
         else if (!strcmp(argv[j], "--aircraft-json")) opt_json = 1;
         else if (!strcmp(argv[j], "--device") && more) cfg.device = atoi(argv[++j]);
+        else if (!strcmp(argv[j], "--gpus") && more) cfg.n_gpus = atoi(argv[++j]);
         else if (!strcmp(argv[j], "--chunk") && more) chunk = (size_t)strtoull(argv[++j], NULL, 10);
         else {
             fprintf(stderr, "Unknown or not enough arguments for option '%s'.\n", argv[j]);

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MODES_B200_ABI_VERSION 1
+#define MODES_B200_ABI_VERSION 2
 
 /* Sizes fixed by the reference's buffering (dump1090.c:54, :61, :331). */
 #define MODES_BUFFER_BYTES    262144      /* MODES_DATA_LEN: new bytes per reference buffer */
@@ -53,6 +53,15 @@ typedef struct modes_config {
     int32_t device;             /* CUDA device ordinal, default 0 */
     int32_t profile;            /* 1: record per-kernel CUDA-event times (modes_get_kernel_times) */
     uint64_t max_batch_bytes;   /* device staging per in-flight batch; 0 = 64 MiB */
+    int32_t n_gpus;             /* 0 or 1: one GPU (`device`).  N > 1: the streaming decode (modes_process /
+                                   modes_finish) deals its batches of whole reference buffers round-robin to N
+                                   devices starting at `device` — one stream, one pinned-to-device copy and
+                                   two staging slots per GPU, every GPU behind its own PCIe link — and the
+                                   calling thread resolves each group of N batches exactly (the speculative
+                                   shard resolve of modes_resolver_run_shards).  With fewer than N devices
+                                   present, devices are reused round-robin.  The stage-level entry points
+                                   stay on `device`. */
+    int32_t reserved;
 } modes_config;
 
 /* Replaces struct modesMessage (dump1090.c:211-260): same field names and
@@ -217,6 +226,9 @@ size_t modes_resolver_output_count(const modes_resolver *r);
  * decodeHexMessage dump1090.c:2472-2502): CRC, fix and field decode run on the
  * device + resolve path with the context's ICAO cache. */
 int  modes_decode_frame(modes_ctx *ctx, const uint8_t msg[14], modes_message *out);
+/* n frames of 14 bytes each in one launch (device staging is kept by the context); decoded in
+ * order, as n calls of modes_decode_frame would. */
+int  modes_decode_frames(modes_ctx *ctx, const uint8_t *frames, size_t n, modes_message *out);
 
 /* ---- presentation -------------------------------- */
 /* The reference's default (non --raw) text for one message: displayModesMessage()

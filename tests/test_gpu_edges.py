@@ -101,6 +101,26 @@ def test_hex_door_matches_reference(gpu_decoder_factory, checker_libs):
             dec.close()
 
 
+def test_hex_door_batch_equals_single_frames(gpu_decoder_factory, checker_libs):
+    """modes_decode_frames(n) == n x modes_decode_frame, including the address cache carried from frame to frame."""
+    rng = synth.Counter(11)
+    frames = []
+    for k in range(300):
+        df = [17, 11, 17, 4, 5, 20, 18, 0][k % 8]
+        icao = 0x400000 + rng.below(40)
+        body = (icao.to_bytes(3, "big") + bytes(rng.below(256) for _ in range(7))) if df in (17, 18) else \
+            (icao.to_bytes(3, "big") if df == 11 else bytes(rng.below(256) for _ in range(10 if df >= 16 else 3)))
+        fr = synth.make_frame(df, rng.below(8), body, icao_for_ap=None if df in (11, 17, 18) else icao)
+        frames.append(synth.flip_bits(fr, [rng.below(len(fr) * 8) for _ in range(k % 3)]))
+    for aggressive in (0, 1):
+        one = gpu_decoder_factory(aggressive=aggressive)
+        many = gpu_decoder_factory(aggressive=aggressive)
+        want = [C.msg_fields(one.decode_frame(f)) for f in frames]
+        got = [C.msg_fields(m) for m in many.decode_frames(frames)]
+        assert got == want
+        assert any(m["crcok"] for m in got if m["msgtype"] in (4, 5, 20))     # address/parity replies validated by the carried cache
+
+
 def test_c_host_binary(checker_libs):
     """./dump1090-b200 --ifile modes1.bin --raw prints the reference's lines (SURVEY.md §4 md5 pins)."""
     exe = ROOT / "dump1090-b200"
@@ -226,6 +246,31 @@ def test_caller_buffers_overflow_is_reported(gpu_decoder_factory):
     dec.detect_device(d.data_ptr(), 1, None, small.data_ptr(), 100, tiles.data_ptr())
     with pytest.raises(RuntimeError, match="capacity exceeded"):
         dec.detect_wait()
+
+
+@pytest.mark.parametrize("n_gpus,batch_buffers", [(2, 1), (3, 2), (2, 256)])
+def test_multi_gpu_context(n_gpus, batch_buffers, gpu_decoder_factory, checker_libs):
+    """modes_config.n_gpus > 1: the streaming decode deals its batches to several GPUs (devices are
+    reused round-robin when the box has fewer) and resolves each group of batches exactly; messages,
+    fields and statistics equal the oracle's, whatever the batch size and the feeding pattern."""
+    data = synth.random_traffic(131072 * 11 + 4321, 2400, 91, n_aircraft=18)
+    for kw in (dict(), dict(aggressive=1, check_crc=0)):
+        exp, st = C.oracle_decode(data, aggressive=kw.get("aggressive", 0), check_crc=kw.get("check_crc", 1), cap=100000)
+        dec = gpu_decoder_factory(n_gpus=n_gpus, max_batch_bytes=batch_buffers * api.BUFFER_BYTES, **kw)
+        got = dec.decode(data)
+        assert _lines(got) == _olines(exp)
+        assert [C.msg_fields(m, with_pos=True) for m in got] == [C.msg_fields(m, with_pos=True) for m in exp]
+        assert list(dec.stats().values()) == st
+        assert _lines(dec.decode(data, chunk=300001)) == _olines(exp)
+
+
+def test_c_host_multi_gpu(checker_libs):
+    """./dump1090-b200 --gpus 2: same lines as one GPU (SURVEY.md §4 md5 pins)."""
+    exe = ROOT / "dump1090-b200"
+    f = str(C.modes1_path())
+    for flags, (n, md5) in {(): (284, "4a81758c8bec"), ("--no-crc-check", "--aggressive"): (824, "bec25488d6b8")}.items():
+        out = subprocess.run([str(exe), "--ifile", f, "--raw", "--gpus", "2", "--chunk", "300000", *flags], capture_output=True, check=True).stdout
+        assert out.count(b"\n") == n and hashlib.md5(out).hexdigest().startswith(md5), flags
 
 
 def test_two_gpu_fused_gather(checker_libs):
