@@ -60,6 +60,7 @@ struct modes_ctx {
     uint16_t *d_lut_iq = nullptr;
     uint32_t *d_bit_syn = nullptr;
     uint32_t *d_fix_hash = nullptr;
+    uint32_t *d_pair_hash = nullptr;
     DeviceTables tab{};
     Slot slot[2];
     Slot detect;                      // stage-level API workspace
@@ -408,7 +409,7 @@ void modes_destroy(modes_ctx *ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->own_detect_stream) { cudaStreamSynchronize(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
-    cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash);
+    cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash); cudaFree(ctx->d_pair_hash);
     cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
     if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
@@ -446,7 +447,11 @@ static int create_impl(modes_ctx *ctx) {
     CK(nullptr, cudaMemcpy(ctx->d_lutn, lutn.data(), kNLutEntries * sizeof(uint16_t), cudaMemcpyHostToDevice));
     CK(nullptr, cudaMemcpy(ctx->d_bit_syn, syn, sizeof(syn), cudaMemcpyHostToDevice));
     CK(nullptr, cudaMemcpy(ctx->d_fix_hash, hash, sizeof(hash), cudaMemcpyHostToDevice));
-    ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_lut_iq, ctx->d_bit_syn, ctx->d_fix_hash};
+    std::vector<uint32_t> pair(kPairHashSlots);
+    if (!build_pair_hash(syn, pair.data())) return fail(nullptr, "internal: two-bit syndrome table construction failed");
+    CK(nullptr, cudaMalloc(&ctx->d_pair_hash, pair.size() * sizeof(uint32_t)));
+    CK(nullptr, cudaMemcpy(ctx->d_pair_hash, pair.data(), pair.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_lut_iq, ctx->d_bit_syn, ctx->d_fix_hash, ctx->d_pair_hash};
     CK(nullptr, cudaMallocHost(&ctx->pending, MODES_BUFFER_BYTES));
     for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->detect})
         if (slot_init(ctx, *s)) { g_create_error = ctx->err; return -1; }

@@ -88,7 +88,20 @@ struct Tables {
     const uint32_t *bit_syn;     // [112]   syndrome of one flipped bit
     const uint32_t *nib_syn;     // [28*16] syndrome of nibble value x at frame nibble i: XOR of bit_syn over its set bits
     const uint32_t *fix_hash;    // [256]   inverse of bit_syn over positions 5..111
+    const uint32_t *pair_hash;   // [1 << kPairHashBits] syndrome of two flipped bits p < q -> p (global memory on the device)
 };
+constexpr int kPairHashBits = 14, kPairHashMaxProbe = 16;
+
+// First flipped bit p of the two-bit pattern with syndrome s, or -1.
+MODES_SERIAL_FN int pair_first(const uint32_t *pair_hash, uint32_t s) {
+    const uint32_t h = (s * 0x9E3779B1u) >> (32 - kPairHashBits);
+    for (int i = 0; i < kPairHashMaxProbe; i++) {
+        const uint32_t e = pair_hash[(h + i) & ((1u << kPairHashBits) - 1u)];
+        if (e == 0xFFFFFFFFu) return -1;
+        if ((e >> 7) == s) return (int)(e & 0x7f);
+    }
+    return -1;
+}
 
 // Index into lut_iq of the sample held in the low (kLutLow) or high (kLutHigh) half of a word of
 // |byte - 127| values: kIqLutStride * |I-127| + |Q-127| as one byte dot product.
@@ -154,14 +167,13 @@ MODES_SERIAL_FN void crc_and_fix(uint32_t F[4], int msgbits, uint32_t msgtype, i
             flip_bit(F, hit - off);
             errorbit = (uint32_t)(hit - off); nfixed = 1; S = 0;
         } else if (aggressive) {
-            // two flipped bits p < q: S ^ syn[p] must be the syndrome of some q; first p wins
-            for (int p = pmin; p < 112; p++) {
+            // two flipped bits p < q (all 5671 patterns have distinct syndromes): p from the pair
+            // table, q as the position whose syndrome is S ^ syn[p]; both must lie in the frame
+            const int p = pair_first(tab.pair_hash, S);
+            if (p >= pmin) {
                 const int q = syndrome_pos(tab.fix_hash, S ^ tab.bit_syn[p]);
-                if (q > p) {
-                    flip_bit(F, p - off); flip_bit(F, q - off);
-                    errorbit = (uint32_t)(p - off); nfixed = 2; S = 0;
-                    break;
-                }
+                flip_bit(F, p - off); flip_bit(F, q - off);
+                errorbit = (uint32_t)(p - off); nfixed = 2; S = 0;
             }
         }
     }

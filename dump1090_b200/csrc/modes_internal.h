@@ -27,6 +27,9 @@ constexpr uint32_t kBufSamples   = MODES_BUFFER_SAMPLES;
 constexpr uint32_t kScanLimit    = kBufSamples - 2;             // j < 131070
 constexpr int      kNLutEntries  = 32769;                       // magnitude by i*i+q*q
 constexpr int      kFixHashSlots = 256;
+constexpr int      kPairHashBits = 14;                          // == serial::kPairHashBits
+constexpr int      kPairHashSlots = 1 << kPairHashBits;          // two-bit patterns: 5671 entries
+constexpr int      kPairHashMaxProbe = 16;                      // checked at table construction
 constexpr int      kLutIqStride  = 136;                         // == serial::kIqLutStride (modes_eval_serial.cuh)
 constexpr int      kLutIqEntries = 129 * kLutIqStride;
 
@@ -35,6 +38,7 @@ struct DeviceTables {
     const uint16_t *lut_iq;      // [129 x kLutIqStride] the same keyed by (|I-127|, |Q-127|); 16-byte aligned
     const uint32_t *bit_syn;     // [112] syndrome of a single flipped bit (dump1090.c:683-698 + parity bits)
     const uint32_t *fix_hash;    // [256] open-addressed inverse of bit_syn: (syndrome<<8 | pos), 0xFFFFFFFF empty
+    const uint32_t *pair_hash;   // [16384] two flipped bits p < q: (syndrome<<7 | p), 0xFFFFFFFF empty
 };
 
 struct BatchView {
@@ -71,6 +75,7 @@ void build_lutn(uint16_t *out /*[32769]*/);
 void build_lut_iq(uint16_t *out /*[kLutIqEntries]*/);
 void build_bit_syndromes(uint32_t *out /*[112]*/);
 bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out /*[256]*/);
+bool build_pair_hash(const uint32_t *bit_syn, uint32_t *out /*[kPairHashSlots]*/);
 
 // ---- sequential resolve (modes_resolve.cpp) --------------------------------
 struct ResolveState {

@@ -493,7 +493,7 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *wwin = s_win + warp * 32 * kSerRow;
     const uint32_t wwin_s = (uint32_t)__cvta_generic_to_shared(wwin);
-    const serial::Tables T{s_lut, s_syn, s_nib, s_hash};
+    const serial::Tables T{s_lut, s_syn, s_nib, s_hash, tab.pair_hash};
     uint32_t n_cand = counters[0];
     if (n_cand > cand_capacity) n_cand = cand_capacity;
     const uint32_t n_chunks = (n_cand + 31) / 32;

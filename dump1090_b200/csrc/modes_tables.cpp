@@ -10,6 +10,9 @@
 //            the 24 parity bits (dump1090.c:738-741)
 //   fix_hash open-addressed inverse of bit_syn over positions 5..111, the domain
 //            of the reference's bitErrorTable (dump1090.c:806)
+//   pair_hash open-addressed map from the syndrome of TWO flipped bits p < q (positions 5..111,
+//            5671 patterns, all syndromes distinct: dump1090.c:817-841) to p; q follows from
+//            fix_hash(S ^ bit_syn[p]).  One or two probes replace a 107-step search per frame.
 #include <cmath>
 #include <cstring>
 #include "modes_internal.h"
@@ -49,6 +52,24 @@ bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out) {
         }
         if (i == kFixHashSlots) return false;
     }
+    return true;
+}
+
+bool build_pair_hash(const uint32_t *bit_syn, uint32_t *out) {
+    std::memset(out, 0xFF, sizeof(uint32_t) * kPairHashSlots);
+    for (int p = 5; p < 112; p++)
+        for (int q = p + 1; q < 112; q++) {
+            const uint32_t s = bit_syn[p] ^ bit_syn[q];
+            if (s == 0 || s >= (1u << 24)) return false;
+            const uint32_t h = (s * 0x9E3779B1u) >> (32 - kPairHashBits);
+            int i = 0;
+            for (; i < kPairHashMaxProbe; i++) {
+                uint32_t &e = out[(h + i) & (kPairHashSlots - 1)];
+                if (e == 0xFFFFFFFFu) { e = (s << 7) | (uint32_t)p; break; }
+                if ((e >> 7) == s) return false;     // two patterns with one syndrome: impossible for this code
+            }
+            if (i == kPairHashMaxProbe) return false;    // the probe bound the kernels rely on
+        }
     return true;
 }
 

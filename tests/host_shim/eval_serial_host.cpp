@@ -12,6 +12,7 @@ void build_lutn(uint16_t *out);
 void build_lut_iq(uint16_t *out);
 void build_bit_syndromes(uint32_t *out);
 bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out);
+bool build_pair_hash(const uint32_t *bit_syn, uint32_t *out);
 }
 
 // virt: the virtual sample array as bytes: 480 halo bytes (2 unused samples + 238 carried) then the body.
@@ -21,6 +22,7 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
     static uint32_t bit_syn[112], fix_hash[256];
     static std::vector<uint32_t> nib_syn(28 * 16);
     static std::vector<uint16_t> lut_iq(kIqLutEntries);
+    static std::vector<uint32_t> pair_hash(1u << kPairHashBits);
     static bool ready = false;
     if (!ready) {
         modes::build_bit_syndromes(bit_syn);
@@ -28,9 +30,10 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
         for (int pos = 0; pos < 28; pos++)
             for (uint32_t v = 0; v < 16; v++) nib_syn[pos * 16 + v] = nibble_syndrome(bit_syn, pos, v);
         modes::build_lut_iq(lut_iq.data());
+        if (!modes::build_pair_hash(bit_syn, pair_hash.data())) return -1;
         ready = true;
     }
-    const Tables tab{lut_iq.data(), bit_syn, nib_syn.data(), fix_hash};
+    const Tables tab{lut_iq.data(), bit_syn, nib_syn.data(), fix_hash, pair_hash.data()};
     auto s16 = [&](uint64_t idx) -> uint32_t { uint16_t w; std::memcpy(&w, virt + 2 * idx, 2); return w; };
     for (uint32_t c = 0; c < n; c++) {
         const uint32_t v = cand_v[c];
