@@ -29,7 +29,7 @@ EVAL_GATE_OK, EVAL_ERRORS, EVAL_DECODED, EVAL_P2_VALID = 1, 2, 4, 8
 class Config(C.Structure):
     _fields_ = [("fix_errors", C.c_int32), ("aggressive", C.c_int32), ("check_crc", C.c_int32),
                 ("drop_eof_buffer", C.c_int32), ("device", C.c_int32), ("profile", C.c_int32),
-                ("max_batch_bytes", C.c_uint64), ("n_gpus", C.c_int32), ("reserved", C.c_int32)]
+                ("max_batch_bytes", C.c_uint64), ("n_gpus", C.c_int32), ("gpu_resolve", C.c_int32)]
 
 
 _MSG_A = ("errorbit aa1 aa2 aa3 phase_corrected ca iid metype mesub heading_is_valid heading "
@@ -204,7 +204,7 @@ def parse_hex_line(line: str | bytes):
 
 
 def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, device=0, profile=0,
-                max_batch_bytes=0, n_gpus=0) -> Config:
+                max_batch_bytes=0, n_gpus=0, gpu_resolve=0) -> Config:
     cfg = Config()
     lib().modes_default_config(C.byref(cfg))
     cfg.fix_errors, cfg.aggressive, cfg.check_crc = int(fix_errors), int(aggressive), int(check_crc)
@@ -212,6 +212,7 @@ def make_config(fix_errors=1, aggressive=0, check_crc=1, drop_eof_buffer=0, devi
     if max_batch_bytes:
         cfg.max_batch_bytes = int(max_batch_bytes)
     cfg.n_gpus = int(n_gpus)
+    cfg.gpu_resolve = int(gpu_resolve)
     return cfg
 
 

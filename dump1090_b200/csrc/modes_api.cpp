@@ -38,6 +38,11 @@ struct Slot {
     modes_candidate *h_records = nullptr; size_t h_records_cap = 0;   // pinned
     modes_tile *h_tiles = nullptr;   size_t h_tiles_cap = 0;          // pinned
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // cfg.gpu_resolve: workspace of the device resolve, sized for gr_buffers buffers / gr.capacity deliveries
+    GpuResolve gr{};
+    size_t gr_buffers = 0;
+    uint32_t *h_gr_flags = nullptr;       // pinned: flags[3] + pad, then stats[8] as u64, then the end cache [1024]
+    modes_delivery *h_deliveries = nullptr; size_t h_deliveries_cap = 0;   // pinned
     // in-flight batch
     bool busy = false;
     size_t n_buffers = 0;
@@ -66,6 +71,11 @@ struct modes_ctx {
     Slot detect;                      // stage-level API workspace
     // cfg.n_gpus > 1: this context is the front of a multi-GPU decode and owns one single-GPU
     // context per device; it keeps the stream state, the resolve state and the outputs itself
+    // cfg.gpu_resolve: the address cache lives on the device, handed from batch to batch
+    uint32_t *d_cache[2] = {nullptr, nullptr};
+    int cache_cur = 0;
+    cudaEvent_t ev_resolved = nullptr;    // the last batch's device resolve has finished (its cache_out is valid)
+    bool resolved_pending = false;
     // hex door staging (modes_decode_frames)
     uint8_t *d_frames = nullptr; modes_frame_eval *d_frame_evals = nullptr, *h_frame_evals = nullptr; size_t frames_cap = 0;
     std::vector<modes_ctx *> gpus;
@@ -130,6 +140,9 @@ void slot_free(Slot &s) {
     cudaFree(s.d_iq); cudaFree(s.d_halo); cudaFree(s.d_cand_v); cudaFree(s.d_records);
     cudaFree(s.d_tiles); cudaFree(s.d_counters);
     cudaFreeHost(s.h_halo); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_records); cudaFreeHost(s.h_tiles);
+    cudaFree(s.gr.start); cudaFree(s.gr.end); cudaFree(s.gr.written); cudaFree(s.gr.readfirst); cudaFree(s.gr.rerun);
+    cudaFree(s.gr.n_deliv); cudaFree(s.gr.offsets); cudaFree(s.gr.flags); cudaFree(s.gr.stats_out); cudaFree(s.gr.out);
+    cudaFreeHost(s.h_gr_flags); cudaFreeHost(s.h_deliveries);
     for (auto &e : s.ev) if (e) cudaEventDestroy(e);
     for (auto &e : s.halo_ev) if (e) cudaEventDestroy(e);
     if (s.stream) cudaStreamDestroy(s.stream);
@@ -178,6 +191,32 @@ int host_ensure(modes_ctx *ctx, Slot &s, size_t n_records, size_t n_tiles) {
 }
 
 int launch_batch(modes_ctx *ctx, Slot &s);
+
+// Workspace of the device resolve for the slot's current batch.
+int gpu_resolve_ensure(modes_ctx *ctx, Slot &s) {
+    const size_t nb = s.n_buffers;
+    if (s.gr_buffers < nb) {
+        cudaFree(s.gr.start); cudaFree(s.gr.end); cudaFree(s.gr.written); cudaFree(s.gr.readfirst); cudaFree(s.gr.rerun);
+        cudaFree(s.gr.n_deliv); cudaFree(s.gr.offsets);
+        s.gr.start = s.gr.end = s.gr.written = s.gr.readfirst = s.gr.rerun = s.gr.n_deliv = s.gr.offsets = nullptr;
+        s.gr_buffers = 0;
+        CK(ctx, cudaMalloc(&s.gr.start, nb * 4096)); CK(ctx, cudaMalloc(&s.gr.end, nb * 4096));
+        CK(ctx, cudaMalloc(&s.gr.written, nb * 128)); CK(ctx, cudaMalloc(&s.gr.readfirst, nb * 128));
+        CK(ctx, cudaMalloc(&s.gr.rerun, nb * 4)); CK(ctx, cudaMalloc(&s.gr.n_deliv, nb * 4)); CK(ctx, cudaMalloc(&s.gr.offsets, (nb + 1) * 4));
+        s.gr_buffers = nb;
+    }
+    if (!s.gr.flags) {
+        CK(ctx, cudaMalloc(&s.gr.flags, 4 * sizeof(uint32_t)));
+        CK(ctx, cudaMalloc(&s.gr.stats_out, 8 * sizeof(uint64_t)));
+        CK(ctx, cudaMallocHost(&s.h_gr_flags, (20 + 1024) * sizeof(uint32_t)));
+    }
+    if (s.gr.capacity < s.cand_cap) {                     // at most two deliveries per candidate; one per candidate is 2x the dense capture
+        cudaFree(s.gr.out); s.gr.out = nullptr; s.gr.capacity = 0;
+        CK(ctx, cudaMalloc(&s.gr.out, (size_t)s.cand_cap * sizeof(modes_delivery)));
+        s.gr.capacity = s.cand_cap;
+    }
+    return 0;
+}
 
 // Queue one batch on the slot's stream: (optional H2D) + halo + scan + frame evaluation.
 int submit(modes_ctx *ctx, Slot &s, const uint8_t *host_iq, const void *d_iq, size_t n_buffers,
@@ -232,6 +271,23 @@ int launch_batch(modes_ctx *ctx, Slot &s) {
     if (pe) CK(ctx, cudaEventRecord(pe[2], s.stream));
     CK(ctx, cudaGetLastError());
     ctx->launches += 2;
+    if (ctx->cfg.gpu_resolve && s.own_outputs && &s != &ctx->detect) {
+        if (gpu_resolve_ensure(ctx, s)) return -1;
+        // the address cache comes from the previous batch's resolve (other slot, other stream)
+        if (ctx->resolved_pending) CK(ctx, cudaStreamWaitEvent(s.stream, ctx->ev_resolved, 0));
+        s.gr.cache_in = ctx->d_cache[ctx->cache_cur];
+        s.gr.cache_out = ctx->d_cache[ctx->cache_cur ^ 1];
+        ctx->cache_cur ^= 1;
+        launch_gpu_resolve(s.gr, s.out_records, s.out_tiles, tiles_for(n_samples), (uint32_t)s.n_buffers, ctx->cfg.check_crc,
+                           ctx->sm_count, s.stream);
+        CK(ctx, cudaGetLastError());
+        ctx->launches += 3 + 2 * kGpuResolveRounds;
+        CK(ctx, cudaEventRecord(ctx->ev_resolved, s.stream));
+        ctx->resolved_pending = true;
+        CK(ctx, cudaMemcpyAsync(s.h_gr_flags, s.gr.flags, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.h_gr_flags + 4, s.gr.stats_out, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaMemcpyAsync(s.h_gr_flags + 20, s.gr.cache_out, 1024 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+    }
     CK(ctx, cudaMemcpyAsync(s.h_counters, s.d_counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaEventRecord(s.ev[3], s.stream));
     s.busy = true;
@@ -245,6 +301,7 @@ int wait_batch(modes_ctx *ctx, Slot &s, uint64_t *n_out) {
     for (;;) {
         CK(ctx, cudaEventSynchronize(s.ev[3]));
         if (!s.h_counters[1] && s.h_counters[0] <= s.out_cap) break;
+        if (ctx->cfg.gpu_resolve && &s != &ctx->detect) break;           // reported by collect(): the device resolve ran on a truncated list
         const uint32_t found = s.h_counters[0];
         if (!s.own_outputs)
             return fail(ctx, "candidate capacity exceeded: %u found, room for %u", found, s.out_cap);
@@ -273,6 +330,27 @@ int collect(modes_ctx *ctx, Slot &s) {
     if (wait_batch(ctx, s, &n)) return -1;
     s.busy = false;                                     // a repeated (overflowed) batch re-arms the flag
     const double t1 = dbg ? now_ms() : 0;
+    if (ctx->cfg.gpu_resolve) {
+        // the verdicts were taken on the device: fetch the deliveries, build the structs
+        if (s.h_counters[1] || s.h_counters[0] > s.out_cap) return fail(ctx, "gpu_resolve: candidate capacity exceeded (%u found)", s.h_counters[0]);
+        if (s.h_gr_flags[0]) return fail(ctx, "gpu_resolve: address caches did not settle in %d rounds", kGpuResolveRounds);
+        if (s.h_gr_flags[1]) return fail(ctx, "gpu_resolve: delivery capacity exceeded (%u messages)", s.h_gr_flags[2]);
+        const size_t nd = s.h_gr_flags[2];
+        if (s.h_deliveries_cap < nd) {
+            cudaFreeHost(s.h_deliveries); s.h_deliveries = nullptr; s.h_deliveries_cap = 0;
+            const size_t cap = nd + nd / 2 + 1024;
+            CK(ctx, cudaMallocHost(&s.h_deliveries, cap * sizeof(modes_delivery)));
+            s.h_deliveries_cap = cap;
+        }
+        if (nd) CK(ctx, cudaMemcpyAsync(s.h_deliveries, s.gr.out, nd * sizeof(modes_delivery), cudaMemcpyDeviceToHost, s.stream));
+        CK(ctx, cudaStreamSynchronize(s.stream));
+        uint64_t st8[8];
+        memcpy(st8, s.h_gr_flags + 4, sizeof(st8));
+        for (int i = 0; i < 8; i++) ctx->rs.stats[i] += (int64_t)st8[i];
+        memcpy(ctx->rs.icao, s.h_gr_flags + 20, sizeof(ctx->rs.icao));    // host copy for the hex door / a later host resolve
+        deliver_gpu(s.h_deliveries, nd, s.buffer_base, ctx->out);
+        return 0;
+    }
     const size_t nt = tiles_for((uint64_t)s.n_buffers * kBufSamples);
     if (host_ensure(ctx, s, n, nt)) return -1;
     if (n) CK(ctx, cudaMemcpyAsync(s.h_records, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
@@ -411,6 +489,8 @@ void modes_destroy(modes_ctx *ctx) {
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
     cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash); cudaFree(ctx->d_pair_hash);
     cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
+    cudaFree(ctx->d_cache[0]); cudaFree(ctx->d_cache[1]);
+    if (ctx->ev_resolved) cudaEventDestroy(ctx->ev_resolved);
     if (ctx->prof_ready) for (auto &trip : ctx->prof_ev) for (auto &e : trip) cudaEventDestroy(e);
     cudaFreeHost(ctx->pending);
     scratch_destroy(ctx->scratch);
@@ -453,6 +533,11 @@ static int create_impl(modes_ctx *ctx) {
     CK(nullptr, cudaMemcpy(ctx->d_pair_hash, pair.data(), pair.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
     ctx->tab = DeviceTables{ctx->d_lutn, ctx->d_lut_iq, ctx->d_bit_syn, ctx->d_fix_hash, ctx->d_pair_hash};
     CK(nullptr, cudaMallocHost(&ctx->pending, MODES_BUFFER_BYTES));
+    if (ctx->cfg.gpu_resolve) {
+        if (ctx->cfg.n_gpus > 1) return fail(nullptr, "gpu_resolve and n_gpus > 1 cannot be combined");
+        for (auto &c : ctx->d_cache) { CK(nullptr, cudaMalloc(&c, 4096)); CK(nullptr, cudaMemset(c, 0, 4096)); }
+        CK(nullptr, cudaEventCreateWithFlags(&ctx->ev_resolved, cudaEventDisableTiming));
+    }
     for (Slot *s : {&ctx->slot[0], &ctx->slot[1], &ctx->detect})
         if (slot_init(ctx, *s)) { g_create_error = ctx->err; return -1; }
     return 0;
@@ -510,6 +595,12 @@ int modes_set_stream(modes_ctx *ctx, void *cuda_stream) {
 int modes_reset(modes_ctx *ctx) {
     if (!ctx) return -1;
     ctx->rs.reset();
+    if (ctx->cfg.gpu_resolve) {
+        cudaSetDevice(ctx->cfg.device);
+        cudaDeviceSynchronize();
+        for (auto &c : ctx->d_cache) cudaMemset(c, 0, 4096);
+        ctx->resolved_pending = false;
+    }
     ctx->pending_len = 0;
     ctx->buffers_done = 0;
     ctx->finished = false;
@@ -746,6 +837,8 @@ int modes_decode_frames(modes_ctx *ctx, const uint8_t *frames, size_t n, modes_m
     // network feeder: no allocation per call)
     if (ctx->frames_cap < n) {
         cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
+    cudaFree(ctx->d_cache[0]); cudaFree(ctx->d_cache[1]);
+    if (ctx->ev_resolved) cudaEventDestroy(ctx->ev_resolved);
         ctx->d_frames = nullptr; ctx->d_frame_evals = nullptr; ctx->h_frame_evals = nullptr; ctx->frames_cap = 0;
         const size_t cap = n < 64 ? 64 : n + n / 2;
         CK(ctx, cudaMalloc(&ctx->d_frames, cap * 14));

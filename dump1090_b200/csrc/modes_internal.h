@@ -77,6 +77,28 @@ void build_bit_syndromes(uint32_t *out /*[112]*/);
 bool build_fix_hash(const uint32_t *bit_syn, uint32_t *out /*[256]*/);
 bool build_pair_hash(const uint32_t *bit_syn, uint32_t *out /*[kPairHashSlots]*/);
 
+// ---- device resolve (modes_resolve_gpu.cu) ----------------------------------
+// One delivered message as the device resolve hands it over: position, the evaluated frame, and
+// what the sequential half decided.  bits = crcok | phase_corrected << 8 | extra_is_ap << 16;
+// extra = DF11 interrogator id, or the address recovered from an address/parity field.
+struct modes_delivery { int64_t t; modes_frame_eval eval; uint32_t extra; uint32_t bits; };
+static_assert(sizeof(modes_delivery) == 40, "delivery record layout");
+constexpr int kGpuResolveRounds = 4;                 // replay + hand-over rounds before the emit pass (two suffice on real traffic)
+
+struct GpuResolve {
+    uint32_t *start, *end;       // [n_buffers][1024] address cache at the start / end of each buffer
+    uint32_t *written, *readfirst;   // [n_buffers][32]  slots a buffer wrote / read before writing
+    uint32_t *rerun, *n_deliv, *offsets;   // [n_buffers] (+1 for offsets)
+    uint32_t *flags;             // [0] a buffer still needed another replay, [1] delivery capacity exceeded, [2] deliveries
+    const uint32_t *cache_in;    // [1024] cache at the start of the batch
+    uint32_t *cache_out;         // [1024] cache at its end
+    uint64_t *stats_out;         // [8]
+    modes_delivery *out;         // deliveries in stream order
+    uint32_t capacity;           // entries of `out`
+};
+void launch_gpu_resolve(const GpuResolve &g, const modes_candidate *records, const modes_tile *tiles, uint32_t n_tiles,
+                        uint32_t n_buffers, int check_crc, int sm_count, cudaStream_t stream);
+
 // ---- sequential resolve (modes_resolve.cpp) --------------------------------
 struct ResolveState {
     uint32_t icao[1024];         // dump1090.c:335: address per slot (TTL: never expires within a run)
@@ -113,6 +135,8 @@ void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards,
 void resolve_tentative(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
                        size_t n_tiles, int64_t buffer_base, ResolveScratch *scratch);
 void resolve_commit(MessageOut &out, ResolveScratch *scratch);
+// Messages from the device resolve's delivery records (structs built in parallel, sink called in order).
+void deliver_gpu(const modes_delivery *d, size_t n, int64_t buffer_base, MessageOut &out);
 // The order-dependent tail of decodeModesMessage + field decode for one evaluated frame.
 int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *out);
 

@@ -341,6 +341,30 @@ static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
     out.count += n;
 }
 
+void deliver_gpu(const modes_delivery *d, size_t n, int64_t buffer_base, MessageOut &out) {
+    auto build = [=](const modes_delivery &x, modes_message *mm) {
+        const bool is_ap = (x.bits >> 16) & 1u;
+        build_message(x.eval, (int)(x.bits & 1u), is_ap ? 0u : x.extra, is_ap ? x.extra : 0u, mm);
+        mm->sample_pos = (buffer_base << 17) + x.t - MODES_CARRY_SAMPLES;
+        mm->phase_corrected = (int)((x.bits >> 8) & 1u);
+    };
+    size_t in_array = 0;
+    if (out.array && out.count < out.capacity) {
+        in_array = out.capacity - out.count < n ? out.capacity - out.count : n;
+        modes_message *base = out.array + out.count;
+        BuildPool::get().run(in_array, [=](size_t b, size_t e) { for (size_t i = b; i < e; i++) build(d[i], base + i); });
+    }
+    if (out.sink) {
+        for (size_t i = 0; i < n; i++) {
+            if (i < in_array) { out.sink(out.user, out.array + out.count + i); continue; }
+            modes_message tmp;
+            build(d[i], &tmp);
+            out.sink(out.user, &tmp);
+        }
+    }
+    out.count += n;
+}
+
 struct ShardRun { ResolveState start, end; std::vector<Delivery> deliveries; };
 struct ResolveScratch { std::vector<Delivery> deliveries; std::vector<ShardRun> runs; };
 ResolveScratch *scratch_create() { return new (std::nothrow) ResolveScratch(); }

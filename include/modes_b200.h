@@ -61,7 +61,14 @@ typedef struct modes_config {
                                    shard resolve of modes_resolver_run_shards).  With fewer than N devices
                                    present, devices are reused round-robin.  The stage-level entry points
                                    stay on `device`. */
-    int32_t reserved;
+    int32_t gpu_resolve;        /* 0 (default): the order-dependent half (retry/skip state machine, ICAO cache,
+                                   statistics: dump1090.c:1769-1791, :898-983) is replayed on the host over the
+                                   candidate records.  1: it runs on the GPU too — one warp per reference buffer,
+                                   address caches handed from buffer to buffer and verified (SURVEY.md §8(f) item
+                                   4) — and only 40-byte records of the delivered messages cross PCIe; the host
+                                   builds the struct fields.  Same messages, same statistics.  Streaming decode
+                                   on one GPU only; a batch denser than one candidate per 64 samples is an error
+                                   in this mode. */
 } modes_config;
 
 /* Replaces struct modesMessage (dump1090.c:211-260): same field names and
