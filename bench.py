@@ -374,7 +374,7 @@ def run_ours(args) -> None:
     msg_cap = int(1.6 * 425744 * (nbytes // GIB)) + 4096 if name != "df17_aggressive" else (nbytes // 1400) * 2 + 4096
     parity = {"checked": False}
     if world == 1:
-        dec2 = api.Decoder(device=local_rank, **cfg)
+        dec2 = api.Decoder(device=local_rank, gpu_resolve=args.gpu_resolve, **cfg)
         out_arr = dec2.set_output_array(msg_cap)
 
         def e2e_step():
@@ -393,6 +393,7 @@ def run_ours(args) -> None:
         # uploads the next step.  No rank handles another rank's data.
         resolver = api.Resolver(**cfg)
         out_arr = resolver.set_output_array(msg_cap)
+        xchg = sharded.ShmExchange(dist, host_group)     # the 4 KiB address caches travel through /dev/shm
         jobs, done = queue.Queue(), queue.Queue()
         rounds_seen, worker_ms = [], []
         pieces = nbytes // host_bytes                    # host staging is 1 GiB: larger shares go up piece by piece
@@ -422,7 +423,7 @@ def run_ours(args) -> None:
                             off_c += c.size; off_p += nt
                     resolver.reset_state()
                     resolver.rearm_output()
-                    info = sharded.resolve_distributed(resolver, cands, tiles, rank * nbuf, dist, host_group)
+                    info = sharded.resolve_distributed(resolver, cands, tiles, rank * nbuf, dist, host_group, exchange=xchg)
                     rounds_seen.append(info["rounds"])
                     worker_ms.append(1e3 * (time.perf_counter() - t0))
                     done.put(None)
@@ -441,23 +442,63 @@ def run_ours(args) -> None:
                     raise err
             return resolver.output_count()
 
+        # Pipeline (one 1 GiB piece per step): while batch i uploads and runs, batch i-1's records
+        # come down the same link in the other direction (copy on a second stream out of a second
+        # set of device buffers) and job i-1 — resolve + message structs — runs on the host thread.
+        dbuf = [(torch.empty(rec_cap * 56, dtype=torch.uint8, device=dev),
+                 torch.empty(api.tiles_for(pbuf) * 8, dtype=torch.uint8, device=dev)) for _ in range(2)]
+        L = api.lib()
+        in_flight = [None]                               # slot of the batch whose kernels are queued
+
+        def fetch(k):
+            n = dec.detect_wait()                        # the batch in slot k has finished
+            cv = land[k][0].array.view(api.CANDIDATE_DTYPE)
+            tv = land[k][1].array.view(api.TILE_DTYPE)
+            return n, cv, tv
+
+        def download(k, n, cv, tv):
+            if n and L.modes_copy_to_host(api.C.c_void_p(cv.ctypes.data), api.C.c_void_p(dbuf[k][0].data_ptr()), n * 56):
+                raise RuntimeError("record download failed")
+            if L.modes_copy_to_host(api.C.c_void_p(tv.ctypes.data), api.C.c_void_p(dbuf[k][1].data_ptr()), tv.nbytes):
+                raise RuntimeError("tile table download failed")
+            return cv[:n], tv
+
+        def hand_over(parts):
+            e2e_join()                                   # the previous job is done on every rank (collective order)
+            slots[0] = parts
+            pending[0] += 1
+            jobs.put(0)
+
         def e2e_step():
+            if pieces > 1:                               # larger shares: piece by piece, no overlap of download and upload
+                parts = []
+                for i in range(pieces):
+                    carry = carry0 if i == 0 else bytes(pinned.array[-api.CARRY_BYTES:])
+                    dec.detect_host(pinned.ptr, pbuf, carry)
+                    if i == 0:
+                        e2e_join()
+                    c, t = dec.detect_fetch_into(land[0][0].array.view(api.CANDIDATE_DTYPE), land[0][1].array.view(api.TILE_DTYPE))
+                    parts.append((c.copy(), t.copy()))
+                slots[0] = parts
+                pending[0] += 1
+                jobs.put(0)
+                return 0
             k = step_no[0] & 1
             step_no[0] += 1
-            parts = []
-            for i in range(pieces):
-                carry = carry0 if i == 0 else bytes(pinned.array[-api.CARRY_BYTES:])
-                dec.detect_host(pinned.ptr, pbuf, carry)
-                if i == 0:
-                    e2e_join()                           # step i-1 resolved on every rank: its landing buffers are free
-                cv = land[k][0].array.view(api.CANDIDATE_DTYPE)
-                tv = land[k][1].array.view(api.TILE_DTYPE)
-                c, t = dec.detect_fetch_into(cv, tv)     # waits for the kernels; D2H over this rank's own link
-                parts.append((c, t) if pieces == 1 else (c.copy(), t.copy()))
-            slots[k] = parts
-            pending[0] += 1
-            jobs.put(k)
+            prev = in_flight[0]
+            got = fetch(prev) if prev is not None else None
+            dec.detect_host(pinned.ptr, pbuf, carry0, dbuf[k][0].data_ptr(), rec_cap, dbuf[k][1].data_ptr())
+            in_flight[0] = k
+            if got is not None:
+                hand_over([download(prev, *got)])
             return 0
+
+        def e2e_flush():
+            prev = in_flight[0]
+            if prev is not None:
+                got = fetch(prev)
+                in_flight[0] = None
+                hand_over([download(prev, *got)])
 
     def run_e2e(n_steps):
         with torch.cuda.stream(stream):
@@ -465,6 +506,8 @@ def run_ours(args) -> None:
             t0 = time.perf_counter()
             for _ in range(n_steps):
                 e2e_step()
+            if world > 1:
+                e2e_flush()
             n = e2e_join()
             barrier()
             return time.perf_counter() - t0, n
@@ -589,10 +632,11 @@ def run_ours(args) -> None:
                     "ms_per_step": round(1e3 * e2e_s / e2e_steps, 3), "slowest_rank": e2e_slow,
                     "h2d_only_ms": round(h2d_only_ms, 3),
                     "h2d_fraction_of_step": round(h2d_only_ms / (1e3 * e2e_s / e2e_steps), 3),
-                    "path": "modes_process()+modes_finish() from pinned host memory" if world == 1 else
+                    "path": ("modes_process()+modes_finish() from pinned host memory"
+                             + (", order-dependent half on the device (gpu_resolve)" if args.gpu_resolve else "")) if world == 1 else
                             "per rank: modes_detect_host (H2D + kernels) + modes_detect_fetch (D2H of its records) + "
-                            "resolve_distributed on its own host thread (gloo: 4 KiB address caches only), pipelined "
-                            "with the next step's upload"},
+                            "resolve_distributed on its own host thread (4 KiB address caches through /dev/shm only); the "
+                            "download of step i-1 and its resolve overlap the upload of step i"},
             "roofline": {"bound": "hbm", "kernel": "scan_kernel (fused magnitude + preamble tests)",
                          "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
@@ -611,6 +655,7 @@ def run_ours(args) -> None:
     if world > 1:
         jobs.put(None)
         dist.barrier()
+        xchg.close()
         dist.destroy_process_group()
 
 
@@ -706,6 +751,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tiled_nofix", choices=list(WORKLOADS) + ["snr_sweep"])
     ap.add_argument("--frames", type=int, default=10000, help="snr_sweep: frames per SNR point (whole job)")
+    ap.add_argument("--gpu-resolve", type=int, default=0, help="N=1 e2e: 1 = the order-dependent half on the GPU too (modes_config.gpu_resolve)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

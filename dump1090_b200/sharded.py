@@ -101,8 +101,69 @@ def resolve_gathered(resolver, gathered, plan) -> None:
     resolver.run_shards(shards)
 
 
+class ShmExchange:
+    """all_gather of small uint32 vectors between the ranks of ONE node through a file in /dev/shm:
+    every rank owns a row [seq, payload...], writes its payload then bumps its sequence number, and
+    polls the others' — microseconds instead of the milliseconds of a gloo ring over loopback
+    (measured: the resolve worker of a 4-rank job spent a third of its time in three gloo
+    all-gathers of 8 KiB).  Create it collectively (the name travels by broadcast_object_list)."""
+
+    def __init__(self, dist, group=None, max_words: int = 2 * 1024):
+        import os
+        import tempfile
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.words = max_words
+        name = [None]
+        if self.rank == 0:
+            fd, path = tempfile.mkstemp(prefix="modes_b200_xchg_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            os.ftruncate(fd, self.world * (2 + max_words) * 4)
+            os.close(fd)
+            name[0] = path
+        dist.broadcast_object_list(name, src=0, group=group)
+        self.path = name[0]
+        self.mem = np.memmap(self.path, dtype=np.uint32, mode="r+", shape=(self.world, 2 + max_words))
+        self.seq = 0
+        dist.barrier(group=group)
+
+    def all_gather(self, vec: np.ndarray) -> np.ndarray:
+        import time
+        assert vec.size <= self.words
+        self.seq += 1
+        row = self.mem[self.rank]
+        row[2: 2 + vec.size] = vec
+        row[1] = vec.size
+        row[0] = self.seq                                   # published last
+        out = np.empty((self.world, vec.size), dtype=np.uint32)
+        deadline = time.perf_counter() + 120.0
+        for r in range(self.world):
+            while self.mem[r, 0] < self.seq:
+                if time.perf_counter() > deadline:
+                    raise TimeoutError("ShmExchange: a rank did not arrive")
+                time.sleep(0)
+            out[r] = self.mem[r, 2: 2 + vec.size]
+        # nobody may overwrite its row before everybody has read it: second phase on the same counters
+        self.seq += 1
+        self.mem[self.rank, 0] = self.seq
+        for r in range(self.world):
+            while self.mem[r, 0] < self.seq:
+                if time.perf_counter() > deadline:
+                    raise TimeoutError("ShmExchange: a rank did not leave")
+                time.sleep(0)
+        return out
+
+    def close(self):
+        import os
+        self.mem = None
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+
+
 def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_base: int, dist=None, group=None,
-                        start_cache=None) -> dict:
+                        start_cache=None, exchange=None) -> dict:
     """Every rank resolves ITS OWN shard (records in its own host memory) and the result is exactly
     the sequential one: no rank sees another rank's records, only 4 KiB address caches travel.
 
@@ -112,7 +173,8 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
     cache); a rank is verified when its guess equals what the previous rank really ended with and
     that rank is verified; unverified ranks run again from the now known cache.  One round is the
     rule, world rounds the worst case.  Then every rank commits (delivers) its own messages.
-    `group` must accept CPU tensors (gloo).  Returns {"rounds", "end_cache" (of the whole job)}."""
+    `group` must accept CPU tensors (gloo); `exchange` (ShmExchange) replaces it for the 4 KiB
+    vectors on one node.  Returns {"rounds", "end_cache" (of the whole job)}."""
     import torch
     world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size(group)
     rank = 0 if world == 1 else dist.get_rank(group)
@@ -123,6 +185,8 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
     def all_gather(vec: np.ndarray) -> np.ndarray:
         if world == 1:
             return vec[None, :]
+        if exchange is not None:
+            return exchange.all_gather(vec)
         t = torch.from_numpy(vec.astype(np.int64))            # gloo has no uint32
         outs = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(outs, t, group=group)

@@ -98,7 +98,7 @@ def _dist_worker(rank, world, port, kind, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        if kind == "wrong_guess":
+        if kind.startswith("wrong_guess"):
             data = _wrong_guess_stream(24)
             total_buffers = 24
         else:
@@ -106,20 +106,24 @@ def _dist_worker(rank, world, port, kind, q):
             total_buffers = data.size // api.BUFFER_BYTES + 1
         plan = sharded.shard_plan(total_buffers, world)
         first, count = plan[rank]
-        cands = C.oracle_scan_candidates(data, drop_eof=1 if kind == "wrong_guess" else 0)
+        cands = C.oracle_scan_candidates(data, drop_eof=1 if kind.startswith("wrong_guess") else 0)
         arr = np.frombuffer(b"".join(bytes(c) for c in cands), dtype=api.CANDIDATE_DTYPE).copy()
         mine = arr[((arr["t"] >> 17) >= first) & ((arr["t"] >> 17) < first + count)].copy()
         mine["t"] -= first << 17
         res = api.Resolver()
         res.set_output_array(100000)
-        info = sharded.resolve_distributed(res, mine, _tiled(mine, count), first, dist)
+        xchg = sharded.ShmExchange(dist) if kind.endswith("_shm") else None
+        info = sharded.resolve_distributed(res, mine, _tiled(mine, count), first, dist, exchange=xchg)
+        if xchg:
+            assert np.array_equal(xchg.all_gather(np.full(7, rank, dtype=np.uint32))[:, 0], np.arange(world))
+            xchg.close()
         n = res.output_count()
         lines = [res._out[i].raw_line() for i in range(n)]
         pos = [int(res._out[i].sample_pos) for i in range(n)]
         everything = [None] * world
         dist.all_gather_object(everything, (lines, pos, list(res.stats().values()), info["rounds"]))
         if rank == 0:
-            exp, exp_stats = C.oracle_decode(data, drop_eof=1 if kind == "wrong_guess" else 0)
+            exp, exp_stats = C.oracle_decode(data, drop_eof=1 if kind.startswith("wrong_guess") else 0)
             got_lines = [l for part in everything for l in part[0]]
             got_pos = [x for part in everything for x in part[1]]
             got_stats = [sum(part[2][i] for part in everything) for i in range(8)]
@@ -129,7 +133,7 @@ def _dist_worker(rank, world, port, kind, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind", [(2, "traffic"), (3, "traffic"), (2, "wrong_guess")])
+@pytest.mark.parametrize("world,kind", [(2, "traffic"), (3, "traffic"), (2, "wrong_guess"), (3, "traffic_shm"), (2, "wrong_guess_shm")])
 def test_every_rank_resolves_its_own_shard(world, kind, checker_libs):
     """sharded.resolve_distributed over gloo: ranks exchange 4 KiB address caches only, never records,
     and the concatenation of their messages is exactly the sequential decode — also when the first
@@ -145,7 +149,7 @@ def test_every_rank_resolves_its_own_shard(world, kind, checker_libs):
         assert p.exitcode == 0
     same_lines, same_pos, same_stats, rounds, n = q.get(timeout=10)
     assert same_lines and same_pos and same_stats and n > 0
-    assert rounds == 2 if kind == "wrong_guess" else 1 <= rounds <= world
+    assert rounds == 2 if kind.startswith("wrong_guess") else 1 <= rounds <= world
 
 
 def test_shard_plan_and_carry():
