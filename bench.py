@@ -277,6 +277,14 @@ def run_ours(args) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         host_group = dist.new_group(backend="gloo")        # 4 KiB address caches between the ranks' host threads
     dev = torch.device("cuda", local_rank)
+    # Several ranks share this host's cores (and its cgroup CPU quota): each takes its share for the
+    # threads that build message structs, and waits for its GPU asleep instead of spinning.
+    host_share = None
+    if world > 1:
+        host_share = max(1, min(16, effective_cores(host_cpu_facts()) // world))
+        os.environ.setdefault("MODES_BUILD_THREADS", str(host_share))
+        if os.environ.get("BENCH_HOST_WAIT", "block") == "block":
+            api.lib().modes_set_host_wait(1)
     numa = {"numa_node": None}
     if os.environ.get("BENCH_NUMA_BIND", "1") != "0":
         numa = sharded.bind_near_gpu(local_rank)              # before any pinned allocation
@@ -646,6 +654,8 @@ def run_ours(args) -> None:
             "cpu_baseline": cpu_baseline,
         }
         if world > 1:
+            out["e2e"]["host_threads_per_rank"] = int(os.environ.get("MODES_BUILD_THREADS", "0")) or None
+            out["e2e"]["host_wait"] = os.environ.get("BENCH_HOST_WAIT", "block")
             out["e2e"]["resolve_rounds_max"] = int(max(rounds_seen)) if rounds_seen else None
             out["e2e"]["resolve_worker_ms_median_rank0"] = round(float(np.median(worker_ms)), 2) if worker_ms else None
         sys.stdout.flush()

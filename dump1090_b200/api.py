@@ -112,7 +112,7 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_set_output", "modes_output_count", "modes_device_alloc", "modes_device_free",
            "modes_ipc_export", "modes_ipc_open", "modes_ipc_close", "modes_copy_to_host", "modes_device_memset",
            "modes_detect_publish_count", "modes_host_alloc",
-           "modes_host_free", "modes_get_kernel_times", "modes_launch_count", "modes_tile_count",
+           "modes_host_free", "modes_get_kernel_times", "modes_launch_count", "modes_tile_count", "modes_set_host_wait",
            "modes_tracker_create", "modes_tracker_destroy", "modes_tracker_update", "modes_tracker_count",
            "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
            "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl"]

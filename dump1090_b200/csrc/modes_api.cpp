@@ -4,6 +4,7 @@
 //
 // No CPU fallback: every entry point that computes runs the CUDA kernels, and
 // modes_create() fails when no device is usable.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -119,6 +120,42 @@ int fail(modes_ctx *ctx, const char *fmt, ...) {
             return fail(ctx, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// How host threads wait for the GPU.  0 (default): the CUDA runtime's own choice, which spins on a
+// many-core host — lowest latency, one core busy per waiting thread.  1: sleep until the GPU signals
+// (events with cudaEventBlockingSync) — for hosts that run more ranks than they have cores to burn,
+// e.g. eight one-GPU processes under a small cgroup CPU quota.  Process-wide; contexts pick it up
+// when they are created.  MODES_HOST_WAIT=block sets the initial value.
+std::atomic<int> g_host_wait{-1};
+
+int host_wait_mode() {
+    int m = g_host_wait.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = std::getenv("MODES_HOST_WAIT");
+        m = (e && (*e == 'b' || *e == 'B' || *e == '1')) ? 1 : 0;
+        g_host_wait.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+
+unsigned event_flags(bool timing) {
+    return (timing ? 0u : (unsigned)cudaEventDisableTiming) | (host_wait_mode() ? (unsigned)cudaEventBlockingSync : 0u);
+}
+
+// cudaStreamSynchronize, or its sleeping equivalent (the stream must belong to the current device).
+cudaError_t wait_stream(cudaStream_t st) {
+    if (!host_wait_mode()) return cudaStreamSynchronize(st);
+    static thread_local cudaEvent_t ev[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaStreamSynchronize(st);
+    if (!ev[dev] && cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming | cudaEventBlockingSync) != cudaSuccess) {
+        ev[dev] = nullptr;
+        (void)cudaGetLastError();
+        return cudaStreamSynchronize(st);
+    }
+    if (cudaEventRecord(ev[dev], st) != cudaSuccess) { (void)cudaGetLastError(); return cudaStreamSynchronize(st); }
+    return cudaEventSynchronize(ev[dev]);
+}
+
 uint32_t default_cand_capacity(uint64_t n_samples) {
     uint64_t c = n_samples / 64 + 4096;
     return c > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)c;
@@ -129,14 +166,14 @@ int slot_init(modes_ctx *ctx, Slot &s) {
     CK(ctx, cudaMalloc(&s.d_halo, kHaloAlloc));
     CK(ctx, cudaMalloc(&s.d_counters, 4 * sizeof(uint32_t)));
     CK(ctx, cudaMallocHost(&s.h_halo, (size_t)kHaloAlloc * Slot::kHaloRing));
-    for (auto &e : s.halo_ev) CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto &e : s.halo_ev) CK(ctx, cudaEventCreateWithFlags(&e, event_flags(false)));
     CK(ctx, cudaMallocHost(&s.h_counters, 4 * sizeof(uint32_t)));
-    for (auto &e : s.ev) CK(ctx, cudaEventCreate(&e));
+    for (auto &e : s.ev) CK(ctx, cudaEventCreateWithFlags(&e, event_flags(true)));
     return 0;
 }
 
 void slot_free(Slot &s) {
-    if (s.stream) cudaStreamSynchronize(s.stream);
+    if (s.stream) wait_stream(s.stream);
     cudaFree(s.d_iq); cudaFree(s.d_halo); cudaFree(s.d_cand_v); cudaFree(s.d_records);
     cudaFree(s.d_tiles); cudaFree(s.d_counters);
     cudaFreeHost(s.h_halo); cudaFreeHost(s.h_counters); cudaFreeHost(s.h_records); cudaFreeHost(s.h_tiles);
@@ -257,7 +294,7 @@ int launch_batch(modes_ctx *ctx, Slot &s) {
     cudaEvent_t *pe = nullptr;
     if (ctx->cfg.profile) {
         if (!ctx->prof_ready) {
-            for (auto &trip : ctx->prof_ev) for (auto &e : trip) CK(ctx, cudaEventCreate(&e));
+            for (auto &trip : ctx->prof_ev) for (auto &e : trip) CK(ctx, cudaEventCreateWithFlags(&e, event_flags(true)));
             ctx->prof_ready = true;
         }
         if (ctx->prof_head - ctx->prof_tail >= (uint64_t)modes_ctx::kProfRing) ctx->prof_tail = ctx->prof_head - modes_ctx::kProfRing + 1;
@@ -343,7 +380,7 @@ int collect(modes_ctx *ctx, Slot &s) {
             s.h_deliveries_cap = cap;
         }
         if (nd) CK(ctx, cudaMemcpyAsync(s.h_deliveries, s.gr.out, nd * sizeof(modes_delivery), cudaMemcpyDeviceToHost, s.stream));
-        CK(ctx, cudaStreamSynchronize(s.stream));
+        CK(ctx, wait_stream(s.stream));
         uint64_t st8[8];
         memcpy(st8, s.h_gr_flags + 4, sizeof(st8));
         for (int i = 0; i < 8; i++) ctx->rs.stats[i] += (int64_t)st8[i];
@@ -355,7 +392,7 @@ int collect(modes_ctx *ctx, Slot &s) {
     if (host_ensure(ctx, s, n, nt)) return -1;
     if (n) CK(ctx, cudaMemcpyAsync(s.h_records, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
     CK(ctx, cudaMemcpyAsync(s.h_tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
-    CK(ctx, cudaStreamSynchronize(s.stream));
+    CK(ctx, wait_stream(s.stream));
     const double t2 = dbg ? now_ms() : 0;
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
     resolve_candidates(ctx->rs, rc, s.h_records, s.h_tiles, nt, s.buffer_base, ctx->out, ctx->scratch);
@@ -390,7 +427,7 @@ int collect_group(modes_ctx *ctx, int parity) {
     }
     for (size_t k = 0; k < n; k++) {
         CK(ctx, cudaSetDevice(ctx->gpus[k]->cfg.device));
-        CK(ctx, cudaStreamSynchronize(ctx->gpus[k]->slot[parity].stream));
+        CK(ctx, wait_stream(ctx->gpus[k]->slot[parity].stream));
     }
     ResolveConfig rc{ctx->cfg.fix_errors, ctx->cfg.aggressive, ctx->cfg.check_crc};
     resolve_shards(ctx->rs, rc, n, cands.data(), tiles.data(), n_tiles.data(), base.data(), ctx->out, ctx->scratch);
@@ -485,7 +522,7 @@ void modes_destroy(modes_ctx *ctx) {
     for (modes_ctx *g : ctx->gpus) modes_destroy(g);
     ctx->gpus.clear();
     cudaSetDevice(ctx->cfg.device);
-    if (ctx->own_detect_stream) { cudaStreamSynchronize(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
+    if (ctx->own_detect_stream) { wait_stream(ctx->detect.stream); ctx->detect.stream = ctx->own_detect_stream; }
     slot_free(ctx->slot[0]); slot_free(ctx->slot[1]); slot_free(ctx->detect);
     cudaFree(ctx->d_lutn); cudaFree(ctx->d_lut_iq); cudaFree(ctx->d_bit_syn); cudaFree(ctx->d_fix_hash); cudaFree(ctx->d_pair_hash);
     cudaFree(ctx->d_frames); cudaFree(ctx->d_frame_evals); cudaFreeHost(ctx->h_frame_evals);
@@ -586,7 +623,7 @@ size_t modes_output_count(const modes_ctx *ctx) { return ctx ? ctx->out.count : 
 
 int modes_set_stream(modes_ctx *ctx, void *cuda_stream) {
     if (!ctx) return -1;
-    if (ctx->detect.busy) cudaStreamSynchronize(ctx->detect.stream);
+    if (ctx->detect.busy) wait_stream(ctx->detect.stream);
     if (!ctx->own_detect_stream) ctx->own_detect_stream = ctx->detect.stream;
     ctx->detect.stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_detect_stream;
     return 0;
@@ -661,7 +698,7 @@ int modes_compute_magnitude(modes_ctx *ctx, const uint8_t *iq, size_t nsamples, 
         ctx->launches++;
         e = cudaMemcpyAsync(mag, d_mag, nsamples * 2, cudaMemcpyDeviceToHost, st);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = wait_stream(st);
     cudaFree(d_iq); cudaFree(d_mag);
     if (e != cudaSuccess) return fail(ctx, "magnitude kernel failed: %s", cudaGetErrorString(e));
     return 0;
@@ -707,7 +744,7 @@ int modes_detect_fetch(modes_ctx *ctx, modes_candidate *candidates, modes_tile *
     if (n && candidates)
         CK(ctx, cudaMemcpyAsync(candidates, s.out_records, n * sizeof(modes_candidate), cudaMemcpyDeviceToHost, s.stream));
     if (tiles) CK(ctx, cudaMemcpyAsync(tiles, s.out_tiles, nt * sizeof(modes_tile), cudaMemcpyDeviceToHost, s.stream));
-    CK(ctx, cudaStreamSynchronize(s.stream));
+    CK(ctx, wait_stream(s.stream));
     return 0;
 }
 
@@ -851,7 +888,7 @@ int modes_decode_frames(modes_ctx *ctx, const uint8_t *frames, size_t n, modes_m
     launch_eval_frames(ctx->d_frames, ctx->d_frame_evals, (uint32_t)n, ctx->tab, ctx->cfg.fix_errors, ctx->cfg.aggressive, st);
     ctx->launches++;
     CK(ctx, cudaMemcpyAsync(ctx->h_frame_evals, ctx->d_frame_evals, n * sizeof(modes_frame_eval), cudaMemcpyDeviceToHost, st));
-    CK(ctx, cudaStreamSynchronize(st));
+    CK(ctx, wait_stream(st));
     for (size_t i = 0; i < n; i++) {                       // in order: the address cache is sequential
         finish_message(ctx->rs, ctx->h_frame_evals[i], &out[i]);
         out[i].sample_pos = -1;
@@ -903,7 +940,13 @@ int modes_copy_to_host(void *dst_host, const void *src_device, size_t nbytes) {
         st_dev = at.device;
     }
     if (cudaMemcpyAsync(dst_host, src_device, nbytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
-    return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+    return wait_stream(st) == cudaSuccess ? 0 : -1;
+}
+
+int modes_set_host_wait(int mode) {
+    if (mode != 0 && mode != 1) return -1;
+    g_host_wait.store(mode, std::memory_order_relaxed);
+    return 0;
 }
 
 int modes_device_memset(void *dst_device, int value, size_t nbytes) {

@@ -24,6 +24,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <sched.h>
 #include <vector>
 #include "modes_internal.h"
 
@@ -200,6 +201,35 @@ static inline void materialise(const Delivery &d, modes_message *mm) {
     mm->phase_corrected = d.phase_corrected;
 }
 
+// Cores this process may actually keep busy: the CPUs it is allowed on, cut down to the CPU-time
+// quota of its control group (a container that sees 128 CPUs but is granted 16 CPUs' worth of time
+// is throttled as a whole when its threads exceed the quota: more threads then means stalls).
+unsigned host_cpu_budget() {
+    unsigned n = std::thread::hardware_concurrency();
+    if (n == 0) n = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+        const unsigned a = (unsigned)CPU_COUNT(&set);
+        if (a >= 1 && a < n) n = a;
+    }
+    long long quota = -1, period = 0;
+    if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {                       // cgroup v2: "<quota|max> <period>"
+        char q[32];
+        if (std::fscanf(f, "%31s %lld", q, &period) == 2 && std::strcmp(q, "max") != 0) quota = std::atoll(q);
+        std::fclose(f);
+    } else {                                                                         // cgroup v1
+        FILE *fq = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r"), *fp = std::fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r");
+        if (fq && fp && std::fscanf(fq, "%lld", &quota) == 1 && std::fscanf(fp, "%lld", &period) == 1) {} else quota = -1;
+        if (fq) std::fclose(fq);
+        if (fp) std::fclose(fp);
+    }
+    if (quota > 0 && period > 0) {
+        const unsigned c = (unsigned)((quota + period - 1) / period);
+        if (c >= 1 && c < n) n = c;
+    }
+    return n;
+}
+
 // A few helper threads for building message structs; created on first use.
 class BuildPool {
   public:
@@ -223,7 +253,7 @@ class BuildPool {
     BuildPool() {
         // message structs are ~200 B of stores each: a handful of threads saturates one socket's
         // write bandwidth.  MODES_BUILD_THREADS overrides (total threads, including the caller).
-        unsigned hw = std::thread::hardware_concurrency();
+        unsigned hw = host_cpu_budget();
         unsigned nw = hw > 32 ? 15 : (hw > 16 ? 7 : (hw > 2 ? hw / 2 - 1 : 0));
         if (const char *e = std::getenv("MODES_BUILD_THREADS")) { int v = std::atoi(e); if (v >= 1 && v <= 256) nw = (unsigned)v - 1; }
         for (unsigned i = 0; i < nw; i++) workers_.emplace_back([this] { loop(); });

@@ -137,20 +137,26 @@ class ShmExchange:
         out = np.empty((self.world, vec.size), dtype=np.uint32)
         deadline = time.perf_counter() + 120.0
         for r in range(self.world):
-            while self.mem[r, 0] < self.seq:
-                if time.perf_counter() > deadline:
-                    raise TimeoutError("ShmExchange: a rank did not arrive")
-                time.sleep(0)
+            self._await(r, deadline, "arrive")
             out[r] = self.mem[r, 2: 2 + vec.size]
         # nobody may overwrite its row before everybody has read it: second phase on the same counters
         self.seq += 1
         self.mem[self.rank, 0] = self.seq
         for r in range(self.world):
-            while self.mem[r, 0] < self.seq:
-                if time.perf_counter() > deadline:
-                    raise TimeoutError("ShmExchange: a rank did not leave")
-                time.sleep(0)
+            self._await(r, deadline, "leave")
         return out
+
+    def _await(self, r: int, deadline: float, what: str):
+        """Poll rank r's sequence number: yield for the first 200 us (ranks in step arrive within
+        microseconds), then sleep between polls — a rank that is a whole upload late must not cost
+        the waiting ranks a core each."""
+        import time
+        t0 = time.perf_counter()
+        while self.mem[r, 0] < self.seq:
+            now = time.perf_counter()
+            if now > deadline:
+                raise TimeoutError(f"ShmExchange: a rank did not {what}")
+            time.sleep(0 if now - t0 < 200e-6 else 100e-6)
 
     def close(self):
         import os

@@ -331,6 +331,15 @@ void  modes_host_free(void *p);
 int  modes_get_kernel_times(modes_ctx *ctx, float ms[4]);
 /* Cumulative count of kernel launches issued by this context. */
 uint64_t modes_launch_count(const modes_ctx *ctx);
+/* How host threads wait for the GPU, process-wide (contexts read it when they are created).
+ * 0 (default): the CUDA runtime's choice — on a many-core host it spins: lowest latency, one core
+ * busy per waiting thread.  1: sleep until the GPU signals (cudaEventBlockingSync): for hosts that
+ * run more GPU processes than they have cores to spare (e.g. one process per GPU under a small
+ * container CPU quota).  The environment variable MODES_HOST_WAIT=block sets the initial value.
+ * The helper threads that build message structs are sized from the CPUs this process may really
+ * use (affinity mask cut down to the cgroup CPU quota); MODES_BUILD_THREADS=<n> overrides, e.g.
+ * quota / ranks for several processes on one host. */
+int  modes_set_host_wait(int mode);
 /* Entries of the tile table of a batch of n_buffers reference buffers. */
 size_t modes_tile_count(size_t n_buffers);
 

@@ -300,3 +300,27 @@ def test_low_snr_detect_rate_identical(snr_db, gpu_decoder_factory, checker_libs
     got = dec.decode(data)
     assert [C.msg_fields(m) for m in got] == [C.msg_fields(m) for m in exp]
     assert list(dec.stats().values()) == st
+
+
+def test_sleeping_host_wait_gives_the_same_messages(gpu_decoder_factory, checker_libs):
+    """modes_set_host_wait(1): contexts created afterwards wait on cudaEventBlockingSync events."""
+    L = api.lib()
+    a = synth.random_traffic(131072 * 5 + 999, 900, 67)
+    want, st = C.oracle_decode(a)
+    assert L.modes_set_host_wait(1) == 0
+    try:
+        dec = gpu_decoder_factory(max_batch_bytes=2 * api.BUFFER_BYTES)
+        for _ in range(2):
+            assert _lines(dec.decode(a)) == _olines(want)
+        assert list(dec.stats().values()) == st
+        n_buf = a.size // api.BUFFER_BYTES + 1                # the stream plus the no-signal EOF buffer
+        padded = np.full(n_buf * api.BUFFER_BYTES, 127, dtype=np.uint8)
+        padded[: a.size] = a
+        dec.detect_host(padded.ctypes.data, n_buf, None)
+        cands, tiles = dec.detect_fetch(n_buf)
+        res = api.Resolver()
+        res.run(cands, tiles)
+        assert _lines(res.take_messages()) == _olines(want)
+        assert int(tiles["count"].sum()) == cands.size > 0
+    finally:
+        assert L.modes_set_host_wait(0) == 0

@@ -225,3 +225,9 @@ def test_two_resolvers_on_two_threads(checker_libs):
         t.join()
     assert not errors
     assert all(x == want for k in range(2) for x in results[k])
+
+
+def test_host_wait_mode_is_validated():
+    L = api.lib()
+    assert L.modes_set_host_wait(2) == -1 and L.modes_set_host_wait(-1) == -1
+    assert L.modes_set_host_wait(1) == 0 and L.modes_set_host_wait(0) == 0
