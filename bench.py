@@ -233,16 +233,37 @@ def so_digest() -> str:
     return hashlib.sha256(Path(api.LIB_PATH).read_bytes()).hexdigest()[:16]
 
 
+SCAN_KERNEL_SOURCES = ("dump1090_b200/csrc/modes_scan2.cu", "dump1090_b200/csrc/modes_scan_core.cuh",
+                       "dump1090_b200/csrc/modes_internal.h")
+
+
+def scan_source_digest() -> str:
+    """sha256 over the files the scan kernel is compiled from and the compiler flags (the .so itself
+    is not reproducible byte for byte: nvcc embeds per-build identifiers, so two builds of the same
+    sources differ in their digests)."""
+    h = hashlib.sha256()
+    for rel in SCAN_KERNEL_SOURCES:
+        h.update((ROOT / rel).read_bytes())
+    for line in (ROOT / "Makefile").read_text().splitlines():
+        if line.startswith(("ARCH", "NVFLAGS")):
+            h.update(line.encode())
+    return h.hexdigest()[:16]
+
+
 def measured_traffic() -> tuple[float | None, str]:
     """DRAM bytes per scan-kernel launch from the committed ncu capture — only if it was taken with
-    the library that is running now (profiles/scan_kernel_traffic.json records the .so digest)."""
+    the scan kernel that is running now: profiles/scan_kernel_traffic.json records the digest of the
+    kernel's sources + compiler flags (and the digest of the .so it was captured with)."""
     tp = ROOT / "profiles" / "scan_kernel_traffic.json"
     if not tp.exists():
         return None, "no capture committed"
     doc = json.loads(tp.read_text())
-    if doc.get("so_sha256_16") != so_digest():
-        return None, f"capture is of another build ({doc.get('so_sha256_16')} != {so_digest()}): re-run scripts/ncu_traffic.sh"
-    return doc.get("dram_bytes_per_launch"), "profiles/scan_kernel_traffic.json (same build)"
+    if doc.get("so_sha256_16") == so_digest():
+        return doc.get("dram_bytes_per_launch"), "profiles/scan_kernel_traffic.json (same library file)"
+    if doc.get("scan_source_sha256_16") == scan_source_digest():
+        return doc.get("dram_bytes_per_launch"), "profiles/scan_kernel_traffic.json (same scan-kernel sources and flags)"
+    return None, (f"capture is of another scan kernel (sources {doc.get('scan_source_sha256_16')} != {scan_source_digest()}): "
+                  "re-run scripts/ncu_traffic.sh")
 
 
 def messages_digest(arr, n: int) -> str:
@@ -650,7 +671,8 @@ def run_ours(args) -> None:
                          "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                          "scan_ms": round(scan_ms, 4), "eval_ms": round(ktimes[1], 4),
-                         "batches_timed": int(ktimes[3]), "library_sha256_16": so_digest()},
+                         "batches_timed": int(ktimes[3]), "library_sha256_16": so_digest(),
+                         "scan_source_sha256_16": scan_source_digest()},
             "cpu_baseline": cpu_baseline,
         }
         if world > 1:
