@@ -1,0 +1,249 @@
+// modes_eval_fused.cu — K2, frame evaluation as ONE walk per candidate (sm_100a).
+//
+// Replaces the body of detectModeS after the preamble test (dump1090.c:1653-1735) and the
+// order-independent half of decodeModesMessage (:1099-1128), like eval_serial_kernel
+// (modes_kernels.cu), with the per-candidate arithmetic of modes_eval_serial.cuh, namespace fused:
+// the first attempt and the phase-corrected retry share one pass over the window, in the retry's
+// walk direction, and nothing is written back.
+//
+// Thread = candidate, warp = 32 consecutive candidates.  What the kernel adds around the walk:
+//  * The walk direction and scale factors depend on eight preamble samples only
+//    (applyPhaseCorrection, :1498-1517).  Each lane's first seven window words are copied to a small
+//    "preamble area" one chunk AHEAD (cp.async, behind the current chunk's evaluation), so that
+//    when a chunk is staged every lane already knows which way it will walk.
+//  * The windows are staged in WALK ORDER: the words of a backwards-walked candidate are written
+//    reversed (the copy is a 4-byte cp.async per word anyway: windows are only 4-byte aligned).
+//    Every lane then reads ascending slots at compile-time offsets; row stride odd: lane l's slot
+//    k sits in bank (stride*l + k) mod 32, conflict free whatever the directions are.
+//  * kParts == 2 stages half a window at a time into the same rows (first 57 slots, then the other
+//    56): 8.4 KB per warp instead of 15.6, 20 warps per SM instead of 12.  The second half's copy
+//    is exposed (it cannot start before all lanes finished the first half) but hits L2 (the
+//    windows were prefetched a chunk earlier) and the other warps of the scheduler cover it.
+//  * Chunks of 32 candidates are handed out from a global counter two ahead, the next chunk's
+//    positions are loaded behind the copies and its windows prefetched into L2, as before.
+#include <cstdint>
+#include <cstdlib>
+#include <cuda_runtime.h>
+#include "modes_internal.h"
+#include "modes_eval_serial.cuh"
+
+namespace modes {
+namespace {
+
+constexpr int kPreStride = 9;                            // words per lane in the preamble area (7 used; odd: conflict free)
+constexpr int kPreWords = 7;
+constexpr int kNibWords = 28 * 16;
+constexpr int kLutWords = serial::kIqLutEntries / 2;
+constexpr int kTableWords = 112 + kFixHashSlots + kNibWords + kLutWords;
+static_assert(serial::kIqLutStride == kLutIqStride && serial::kIqLutEntries % 8 == 0, "table geometry");
+static_assert(kTableWords % 2 == 0, "record staging uses 8-byte stores");
+
+template <int kParts> struct Geom {
+    static constexpr int kPart0 = kParts == 1 ? serial::fused::kSlots : 57;          // slots staged first
+    static constexpr int kRow = kPart0;                                                // 113 or 57 words: odd
+    static constexpr int kWarps = kParts == 1 ? 12 : 20;
+    static constexpr int kThreads = 32 * kWarps;
+    static constexpr int kWarpWords = 32 * kRow + 32 * kPreStride;
+    static constexpr int kSmemBytes = 4 * (kTableWords + kWarps * kWarpWords);
+    static_assert(kRow % 2 == 1 && 32 * kRow >= 32 * 14 && (32 * kRow) % 2 == 0 && kWarpWords % 2 == 0, "row geometry");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+};
+
+__device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
+    const uint8_t *p = (v < (uint64_t)kHaloSamples) ? in.halo + 2 * v : in.body + 2 * (v - kHaloSamples);
+    return *reinterpret_cast<const uint16_t *>(p);
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t dst_shared, const uint32_t *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+
+// Word w (0..120) of the window of the candidate at virtual position v, whatever it overlaps.
+__device__ __noinline__ uint32_t window_word_slow(const uint8_t *body, const uint8_t *halo, uint64_t n_samples, uint32_t v, int w) {
+    const BatchView in{body, halo, n_samples};
+    if (v > (uint32_t)kHaloSamples)
+        return __ldg(reinterpret_cast<const uint32_t *>(in.body) + ((v - 1 - kHaloSamples) >> 1) + w);
+    // window reaches into the carry block (first 240 positions of a batch): sample by sample, odd = 0
+    return raw_sample(in, (uint64_t)v - 1 + 2 * w) | (raw_sample(in, (uint64_t)v + 2 * w) << 16);
+}
+
+// The first seven window words of this lane's candidate -> its row of the preamble area.
+__device__ __forceinline__ void prestage(const BatchView &in, const uint32_t *body32, uint32_t v, uint32_t *pre, uint32_t pre_s) {
+    if (v > (uint32_t)kHaloSamples) {
+        const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
+#pragma unroll
+        for (int k = 0; k < kPreWords; k++) cp_async4(pre_s + 4u * k, wp + k);
+    } else {
+        for (int k = 0; k < kPreWords; k++) pre[k] = window_word_slow(in.body, in.halo, in.n_samples, v, k);
+    }
+}
+
+// Slots [u0, u0 + count) of all 32 rows of a chunk -> shared memory (row c at rows + c * kRow,
+// slot u at word u - u0).  Forwards slot u = window word 8 + u, backwards = window word 120 - u.
+template <int kRow>
+__device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *body32, uint32_t my_v, uint32_t rev_mask, bool fast,
+                                           uint32_t *rows, uint32_t rows_s, int u0, int count, int lane) {
+    if (fast) {
+        // common case (no window in the carry block): asynchronous copies straight into shared
+        // memory, all 32 rows in flight, one wait (the caller's)
+#pragma unroll 4
+        for (int c = 0; c < 32; c++) {
+            const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
+            const bool rev = (rev_mask >> c) & 1u;
+            const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
+            // word of slot u0 + lane, and the step to the word of slot u0 + lane + 32
+            const uint32_t *src = rev ? wp + (120 - u0 - lane) : wp + (8 + u0 + lane);
+            const int step = rev ? -32 : 32;
+            const uint32_t dst = rows_s + 4u * (uint32_t)(c * kRow + lane);
+            cp_async4(dst, src);
+            if (lane + 32 < count) cp_async4(dst + 128u, src + step);
+            if (count > 64 && lane + 64 < count) cp_async4(dst + 256u, src + 2 * step);
+            if (count > 96 && lane + 96 < count) cp_async4(dst + 384u, src + 3 * step);
+        }
+    } else {
+        for (int c = 0; c < 32; c++) {
+            const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
+            const bool rev = (rev_mask >> c) & 1u;
+            for (int k = lane; k < count; k += 32) {
+                const int u = u0 + k;
+                rows[c * kRow + k] = window_word_slow(in.body, in.halo, in.n_samples, v, rev ? 120 - u : 8 + u);
+            }
+        }
+    }
+}
+
+template <int kParts>
+__global__ void __launch_bounds__(Geom<kParts>::kThreads, 1)
+eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
+                  uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive, uint32_t c_one,
+                  uint32_t c_m1, uint32_t c_m16k) {
+    using G = Geom<kParts>;
+    namespace fz = serial::fused;
+    extern __shared__ __align__(16) uint32_t s_mem[];
+    uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_nib = s_hash + kFixHashSlots;
+    uint16_t *s_lut = reinterpret_cast<uint16_t *>(s_nib + kNibWords);
+    uint32_t *s_warp = s_nib + kNibWords + kLutWords;
+    for (int i = threadIdx.x; i < 112; i += G::kThreads) s_syn[i] = tab.bit_syn[i];
+    for (int i = threadIdx.x; i < kFixHashSlots; i += G::kThreads) s_hash[i] = tab.fix_hash[i];
+    for (int i = threadIdx.x; i < serial::kIqLutEntries / 8; i += G::kThreads)
+        reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(tab.lut_iq) + i);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kNibWords; i += G::kThreads) s_nib[i] = serial::nibble_syndrome(s_syn, i >> 4, i & 15);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *rows = s_warp + warp * G::kWarpWords;
+    uint32_t *pre = rows + 32 * G::kRow + kPreStride * lane;
+    const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(rows);
+    const uint32_t pre_s = (uint32_t)__cvta_generic_to_shared(pre);
+    const serial::Tables T{s_lut, s_syn, s_nib, s_hash, tab.pair_hash};
+    const fz::Lut lut{(uint32_t)__cvta_generic_to_shared(s_lut)};
+    uint32_t n_cand = counters[0];
+    if (n_cand > cand_capacity) n_cand = cand_capacity;
+    const uint32_t n_chunks = (n_cand + 31) / 32;
+    const uint32_t total_warps = gridDim.x * G::kWarps;
+    const uint32_t *body32 = reinterpret_cast<const uint32_t *>(in.body);
+
+    // (The counter values are used untouched until a chunk later: arithmetic on them right away
+    // would wait for the atomic's round trip.)
+    uint32_t chunk = blockIdx.x * G::kWarps + warp;
+    uint32_t next1 = 0, ahead_raw = 0;
+    if (lane == 0) next1 = atomicAdd(&counters[3], 1u);
+    next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
+    uint32_t my_v = 0;
+    if (chunk < n_chunks) {
+        const uint32_t n0 = n_cand - chunk * 32 < 32u ? n_cand - chunk * 32 : 32u;
+        my_v = cand_v[chunk * 32 + ((uint32_t)lane < n0 ? lane : n0 - 1)];
+        prestage(in, body32, my_v, pre, pre_s);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    while (chunk < n_chunks) {
+        if (lane == 0) ahead_raw = atomicAdd(&counters[3], 1u);
+        const uint32_t base = chunk * 32;
+        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;   // idle lanes of the last chunk duplicate its last candidate
+        uint32_t v_next = 0;
+
+        // this lane's walk: direction, factors, byte selector (its preamble words arrived a chunk ago)
+        const uint32_t odd = my_v > (uint32_t)kHaloSamples ? ((my_v - 1 - kHaloSamples) & 1u) : 0u;
+        fz::Lane L;
+        fz::phase_setup(pre, odd, s_lut, c_one, c_m1, c_m16k, L);
+        const uint32_t rev_mask = __ballot_sync(0xffffffffu, L.fwd == 0u);
+        const bool fast = __all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples);
+
+        stage_part<G::kRow>(in, body32, my_v, rev_mask, fast, rows, rows_s, 0, G::kPart0, lane);
+        if (next1 < n_chunks) {                            // the next chunk's positions: loaded behind the copies, used a chunk later
+            const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
+            v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        if (next1 < n_chunks) {
+            // the next chunk: preamble words on their way behind this chunk's evaluation, windows -> L2
+            // (484 bytes from a 4-byte aligned address: five 128-byte lines)
+            prestage(in, body32, v_next, pre, pre_s);
+            if (v_next > (uint32_t)kHaloSamples) {
+                const uint8_t *wp = in.body + 4ull * ((v_next - 1 - kHaloSamples) >> 1);
+                if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
+#pragma unroll
+                    for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
+                }
+            }
+        }
+
+        const uint32_t *row = rows + lane * G::kRow;
+        fz::Walk W;
+        fz::walk_begin(W, L, row[0]);
+        if constexpr (kParts == 1) {
+            fz::walk_blocks(W, L, row, 0, fz::kBlocks, lut);
+        } else {
+            fz::walk_blocks(W, L, row, 0, 2, lut);
+            __syncwarp();                                  // every lane is done with the first half
+            stage_part<G::kRow>(in, body32, my_v, rev_mask, fast, rows, rows_s, G::kPart0, fz::kSlots - G::kPart0, lane);
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            fz::walk_blocks(W, L, row - G::kPart0, 2, fz::kBlocks, lut);
+        }
+        uint32_t rec[14];
+        const uint64_t t = (uint64_t)my_v - 2;
+        rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
+        fz::walk_finish(W, L, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive, T, rec + 2);
+        __syncwarp();
+        if ((uint32_t)lane < n) {
+#pragma unroll
+            for (int k = 0; k < 14; k += 2) *reinterpret_cast<uint2 *>(rows + 14 * lane + k) = make_uint2(rec[k], rec[k + 1]);
+        }
+        __syncwarp();
+        uint32_t *dst = reinterpret_cast<uint32_t *>(records + base);
+        for (uint32_t i = lane; i < n * 14; i += 32) dst[i] = rows[i];
+        asm volatile("cp.async.wait_all;" ::: "memory");   // the next chunk's preamble words
+        __syncwarp();
+        chunk = next1;
+        my_v = v_next;
+        next1 = total_warps + __shfl_sync(0xffffffffu, ahead_raw, 0);
+    }
+}
+
+template <int kParts>
+void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
+                  int fix_errors, int aggressive, int sm_count, cudaStream_t stream) {
+    using G = Geom<kParts>;
+    // the opt-in to > 48 KB of dynamic shared memory is per device
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
+        cudaFuncSetAttribute(eval_fused_kernel<kParts>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+    eval_fused_kernel<kParts><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
+                                                                               records, fix_errors, aggressive, 1u, 0xffffffffu, (uint32_t)-16384);
+}
+
+}  // namespace
+
+void launch_eval_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
+                       int fix_errors, int aggressive, int sm_count, int parts, cudaStream_t stream) {
+    if (parts == 2) launch_fused<2>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    else launch_fused<1>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+}
+
+}  // namespace modes

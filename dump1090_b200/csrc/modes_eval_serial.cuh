@@ -485,5 +485,275 @@ MODES_SERIAL_FN void evaluate(uint32_t *win, uint32_t odd, bool at_buffer_start,
     eval_words(P2, rec + 6);
 }
 
+
+// ================================================================================================
+// Fused single sweep (eval_fused_kernel, modes_eval_fused.cu).
+//
+// The first attempt and the phase-corrected retry read the same 112 sample pairs; what differs is
+// a handful of integer operations per pair.  Which way the retry walks (dump1090.c:1517 / :1537)
+// and its two scale factors depend only on eight preamble samples, so they are known BEFORE any
+// bit is looked at.  One walk in the retry's direction therefore serves both attempts: per pair
+// the two magnitudes are looked up once, the first attempt's "definite" and "greater" flags and
+// the retry's "definite" and "one" flags are shifted into four mask words (the sign bit of a
+// difference goes into the mask with one funnel shift), and the only serial dependency left is
+// the retry's previous decision.  The copy rule of :1675 ("an indefinite bit repeats the bit
+// before it") is applied afterwards on the masks (fill_copies), for both attempts and in either
+// walk direction.  Nothing is written back to the window.
+//
+// The window is handed over in WALK ORDER: the kernel stages a backwards-walked candidate's words
+// reversed, so every lane reads ascending slots and only a per-lane byte selector tells the four
+// cases (direction x odd alignment) apart.
+namespace fused {
+
+#if defined(__CUDA_ARCH__)
+MODES_SERIAL_FN uint32_t perm2(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+MODES_SERIAL_FN uint32_t push_sign(uint32_t acc, uint32_t v) { return __funnelshift_l(v, acc, 1); }   // acc << 1 | sign(v)
+// The (|I-127|, |Q-127|) magnitude table in shared memory, by its 32-bit shared address: the
+// entry's byte address base + 2 * (136 i + q) is two chained byte dot products (FMA pipe; the
+// walk is bound by the integer ALU pipe, where "index * 2 + base" would otherwise go).
+// a * b + c as one multiply-add on the FMA pipe (b is a register the compiler cannot see through)
+MODES_SERIAL_FN uint32_t mad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+struct Lut { uint32_t base; };
+MODES_SERIAL_FN uint32_t lut_at(Lut l, uint32_t a, uint32_t weights) {
+    const uint32_t addr = __dp4a(a, weights, __dp4a(a, weights, l.base));
+    uint16_t v;
+    asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+#else
+MODES_SERIAL_FN uint32_t perm2(uint32_t a, uint32_t b, uint32_t sel) {
+    const uint64_t ab = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((ab >> (8 * ((sel >> (4 * k)) & 7u))) & 0xffu) << (8 * k);
+    return r;
+}
+MODES_SERIAL_FN uint32_t push_sign(uint32_t acc, uint32_t v) { return (acc << 1) | (v >> 31); }
+MODES_SERIAL_FN uint32_t mad(uint32_t a, uint32_t b, uint32_t c) { return a * b + c; }
+struct Lut { const uint16_t *base; };
+MODES_SERIAL_FN uint32_t lut_at(Lut l, uint32_t a, uint32_t weights) { return l.base[dot4(a, weights)]; }
+#endif
+
+// A candidate's walk: slots[0] is the word the first pair starts in; step t (t = 0..111) reads
+// slots[t + 1].  Forwards, slots[u] = window word 8 + u; backwards, slots[u] = window word 120 - u.
+constexpr int kSlots = 113;
+constexpr int kBlockBits = 28, kBlocks = 4;             // 112 bits = 4 blocks of 28 (one mask word each)
+
+struct Lane {
+    uint32_t sel;                // byte selector: (previous slot, this slot) -> (near sample | far sample << 16), raw I/Q
+    uint32_t sgn, k;             // forwards 1, -16384; backwards -1, -1: the retry decides "one" <=> sgn * T + k >= 0
+    uint32_t f_one, f_zero;      // scale factor after a decided one / zero
+    uint32_t fwd;                // 1 forwards
+    uint32_t c_one, c_m1, c_m16k;   // 1, -1, -16384 in registers: multipliers that keep additions on the FMA pipe
+};
+
+// applyPhaseCorrection's preamble measurements (dump1090.c:1498-1517): walk direction and scale
+// factors from window samples m[-1], m[0], m[2], m[3], m[6], m[7], m[9], m[10].  `pre` = the first
+// seven words of the window (forward order), `odd` as in the window layout above.
+// `c_one`, `c_m1`, `c_m16k` = 1, -1, -16384 as values the compiler cannot see (kernel parameters).
+MODES_SERIAL_FN void phase_setup(const uint32_t *pre, uint32_t odd, const uint16_t *lut_iq, uint32_t c_one, uint32_t c_m1,
+                                 uint32_t c_m16k, Lane &L) {
+    const uint32_t m_1 = magnitude_of(lut_iq, window_sample(pre, odd, 0));
+    const uint32_t m0 = magnitude_of(lut_iq, window_sample(pre, odd, 1));
+    const uint32_t m2 = magnitude_of(lut_iq, window_sample(pre, odd, 3));
+    const uint32_t m3 = magnitude_of(lut_iq, window_sample(pre, odd, 4));
+    const uint32_t m6 = magnitude_of(lut_iq, window_sample(pre, odd, 7));
+    const uint32_t m7 = magnitude_of(lut_iq, window_sample(pre, odd, 8));
+    const uint32_t m9 = magnitude_of(lut_iq, window_sample(pre, odd, 10));
+    const uint32_t m10 = magnitude_of(lut_iq, window_sample(pre, odd, 11));
+    const uint32_t on_time = m0 + m2 + m7 + m9;
+    const uint32_t early = (m_1 + m6) * 2u, late = (m3 + m10) * 2u;
+    const bool fwd = !(early > late);                    // early > late: walk backwards (:1517)
+    const uint32_t lead = fwd ? late : early;
+    const uint32_t den = lead + on_time;
+    const uint32_t q = den ? 16384u * lead / den : 0u;   // den > 0 for every real candidate (m0 > m1 >= 0)
+    const uint32_t up = (16384u + q) & 0xffffu, down = (16384u - q) & 0xffffu;
+    // forwards a previous 1 scales the next first half-bit up, backwards a following 1 scales the
+    // previous second half-bit down
+    // (opaque: the walk should multiply by these registers, not re-derive them from `fwd` and `q`
+    // with selects and negations inside its loop)
+    L.f_one = opaque(fwd ? up : down); L.f_zero = opaque(fwd ? down : up);
+    L.fwd = fwd ? 1u : 0u;
+    L.sgn = opaque(fwd ? 1u : 0xffffffffu);
+    L.k = opaque(fwd ? (uint32_t)-16384 : 0xffffffffu);
+    L.c_one = c_one; L.c_m1 = c_m1; L.c_m16k = c_m16k;
+    // near = the half-bit sample next to the previous decision (the one the retry rescales)
+    //   forwards : near = first sample of the pair, far = second
+    //   backwards: near = second sample, far = first
+    L.sel = fwd ? (odd ? 0x7654u : 0x5432u) : (odd ? 0x1032u : 0x7610u);
+}
+
+struct Sweep {
+    uint32_t wo;                 // previous slot
+    uint32_t one;                // the retry's previous decision
+    uint32_t dsum;               // sum of |first - second| over the pairs walked so far (:1714-1717)
+};
+
+// 28 pairs.  First attempt: g1 = near > far, nd1 = |near - far| < 256 (an indefinite bit, :1675);
+// retry: gp2 / lp2 = the rescaled near sample exceeds far / far exceeds it by 256 or more.  Step t
+// ends up at bit 27 - t of each word.  c1 = near - far uncorrected and c2 = the retry's decision
+// value U of the block's first pair (`_first`) and last pair (`_last`): frame bit 0 is one of them.
+//
+// The retry in the scaled domain.  scaleSample (:1473) gives near' = min(floor(P / 2^14), 65535),
+// P = near * factor < 2^31.  Magnitudes are below 65535 - 256, so with T = P - far * 2^14:
+//     near' >  far        <=>  T >= 2^14          far  >  near'       <=>  T < 0
+//     near' -  far >= 256 <=>  T >= 2^22          far  -  near' >= 256 <=>  T < -255 * 2^14
+//     near' == far        <=>  0 <= T < 2^14
+// (the clamp never matters: every threshold on the right is below 65535).  The decision "one"
+// (forwards near' > far, backwards far > near') is U = sgn * T + k >= 0 with (sgn, k) = (1, -2^14)
+// or (-1, -1); a tie is -2^14 <= U < 0 either way.  No shift, no clamp, and the serial chain from
+// one decision to the next is multiply-add, multiply-add, multiply-add, compare, select.
+//
+// Pipes.  An sm_100 scheduler's integer ALU pipe and FMA pipe each take a warp instruction every
+// second cycle; the walk is ALU-heavy by nature (funnel shifts, byte permutes, absolute
+// differences), so every addition that can be a multiply-add with a register multiplier is one:
+// per pair 10 ALU + 10 FMA + 3 load instructions.
+MODES_SERIAL_FN void sweep_block(const uint32_t *slot, const Lane &L, Lut lut, Sweep &S, uint32_t &g1, uint32_t &nd1,
+                                 uint32_t &gp2, uint32_t &lp2, uint32_t &c1_first, uint32_t &c2_first, uint32_t &c1_last,
+                                 uint32_t &c2_last) {
+    uint32_t a_g1 = 0, a_nd1 = 0, a_gp2 = 0, a_lp2 = 0;
+#pragma unroll
+    for (int t = 0; t < kBlockBits; t++) {
+        const uint32_t wn = slot[t + 1];
+        const uint32_t a = absdiff127x4(perm2(S.wo, wn, L.sel));
+        S.wo = wn;
+        const uint32_t X = lut_at(lut, a, kLutLow);       // near
+        const uint32_t Y = lut_at(lut, a, kLutHigh);      // far
+        // first attempt (:1667-1690)
+        S.dsum = absdiff_add(X, Y, S.dsum);
+        const uint32_t c1 = mad(Y, L.c_m1, X);            // near - far
+        a_g1 = push_sign(a_g1, mad(X, L.c_m1, Y));        // far - near < 0
+        a_nd1 = push_sign(a_nd1, absdiff_add(X, Y, 0xffffff00u));          // |near - far| - 256 < 0
+        // retry (:1498-1558, then the same slicing): the near sample is rescaled by the factor the
+        // previous decision selects
+        const uint32_t P = X * (S.one ? L.f_one : L.f_zero);
+        const uint32_t T = mad(Y, L.c_m16k, P);
+        const uint32_t U = mad(T, L.sgn, L.k);
+        S.one = (uint32_t)((int32_t)U >= 0);
+        a_gp2 = push_sign(a_gp2, mad(T, L.c_m1, 0x3fffffu));               // T >= 2^22
+        a_lp2 = push_sign(a_lp2, mad(T, L.c_one, 255u * 16384u));          // T < -255 * 2^14
+        if (t == 0) { c1_first = c1; c2_first = U; }
+        if (t == kBlockBits - 1) { c1_last = c1; c2_last = U; }
+    }
+    g1 = a_g1; nd1 = a_nd1; gp2 = a_gp2; lp2 = a_lp2;
+}
+
+// Four block words (step t of block k at bit 27 - t of w[k]) -> the 112-bit mask in frame order.
+MODES_SERIAL_FN void frame_order(const uint32_t w[kBlocks], uint32_t fwd, uint32_t M[4]) {
+    uint32_t g[kBlocks];
+#pragma unroll
+    for (int j = 0; j < kBlocks; j++) g[j] = fwd ? (bitrev(w[j]) >> 4) : w[kBlocks - 1 - j];
+    M[0] = g[0] | (g[1] << 28);
+    M[1] = (g[1] >> 4) | (g[2] << 24);
+    M[2] = (g[2] >> 8) | (g[3] << 20);
+    M[3] = g[3] >> 12;
+}
+
+// The walk's state between blocks: the eval_fused_kernel variant that stages half a window at a
+// time runs blocks 0-1, restages, then runs blocks 2-3.
+struct Walk {
+    Sweep S;
+    uint32_t G1[kBlocks], ND1[kBlocks], GP2[kBlocks], LP2[kBlocks];
+    uint32_t c1f, c2f, c1l, c2l, dhalf;
+};
+
+MODES_SERIAL_FN void walk_begin(Walk &W, const Lane &L, uint32_t slot0) {
+    W.S.wo = slot0;
+    W.S.one = L.fwd;                                     // the first pair handled always scales up (:1523, :1544): forwards f_one, backwards f_zero
+    W.S.dsum = 0;
+#pragma unroll
+    for (int j = 0; j < kBlocks; j++) W.G1[j] = W.ND1[j] = W.GP2[j] = W.LP2[j] = 0u;
+    W.c1f = W.c2f = W.c1l = W.c2l = W.dhalf = 0u;
+}
+
+// Blocks k0 .. k1-1; `slots` is indexed as the whole walk (slots[28k + t + 1] is read).
+MODES_SERIAL_FN void walk_blocks(Walk &W, const Lane &L, const uint32_t *slots, int k0, int k1, Lut lut) {
+#pragma unroll 1
+    for (int k = k0; k < k1; k++) {
+        uint32_t g1, nd1, gp2, lp2, a, b, c, d;
+        sweep_block(slots + kBlockBits * k, L, lut, W.S, g1, nd1, gp2, lp2, a, b, c, d);
+        // no dynamic register indexing
+#pragma unroll
+        for (int j = 0; j < kBlocks; j++) {
+            W.G1[j] = k == j ? g1 : W.G1[j]; W.ND1[j] = k == j ? nd1 : W.ND1[j];
+            W.GP2[j] = k == j ? gp2 : W.GP2[j]; W.LP2[j] = k == j ? lp2 : W.LP2[j];
+        }
+        if (k == 0) { W.c1f = a; W.c2f = b; }
+        if (k == 1) W.dhalf = W.S.dsum;                  // the first 56 pairs of the walk
+        W.c1l = c; W.c2l = d;
+    }
+}
+
+// Masks -> both attempts' verdicts; rec: the 12 words of pass[0] and pass[1] of the modes_candidate.
+MODES_SERIAL_FN void walk_finish(const Walk &W, const Lane &L, bool at_buffer_start, int fix_errors, int aggressive,
+                                 const Tables &tab, uint32_t rec[12]) {
+    const uint32_t d112 = W.S.dsum;
+    const uint32_t d56 = L.fwd ? W.dhalf : d112 - W.dhalf;   // bits 0..55 (:1716)
+    // frame bit 0 is the walk's first pair forwards, its last pair backwards
+    const int32_t c1 = (int32_t)(L.fwd ? W.c1f : W.c1l), c2 = (int32_t)(L.fwd ? W.c2f : W.c2l);
+    const uint32_t tri1 = c1 == 0;                       // first pair is a tie: bits[0] == 2 (:1681)
+    const uint32_t tri2 = c2 < 0 && c2 >= -16384;        // see sweep_block
+    const uint32_t one0 = L.fwd ? (uint32_t)(c1 > 0) : (uint32_t)(c1 < 0);   // first > second (backwards near = second)
+    const uint32_t one0_retry = (uint32_t)(c2 >= 0);
+
+    uint32_t Gp[4], Lp[4], D[4], O[4], F[4];
+    frame_order(W.G1, L.fwd, Gp);
+    frame_order(W.ND1, L.fwd, Lp);
+    // definite = the halves differ by 256 or more; bit 0 is always taken (:1675).  Backwards near/far
+    // = second/first: on a definite pair first > second <=> !(near > far).
+    const uint32_t flip = L.fwd ? 0u : 0xffffffffu;
+    D[0] = ~Lp[0] | 1u; D[1] = ~Lp[1]; D[2] = ~Lp[2]; D[3] = ~Lp[3] & 0x0000ffffu;
+#pragma unroll
+    for (int j = 0; j < 4; j++) O[j] = D[j] & (Gp[j] ^ flip);                // first > second
+    O[0] = (O[0] & ~1u) | one0;
+    fill_copies(D, O, F);
+    if (tri1) spread_tie_mask(D, F);
+
+    Verdict P1, P2;
+    judge_sliced(F, tri1, d56, d112, fix_errors, aggressive, tab, P1);
+    P2.F[0] = P2.F[1] = P2.F[2] = P2.F[3] = 0;
+    P2.msgtype = 0; P2.flags = 0; P2.errorbit = 0; P2.nfixed = 0; P2.crc = 0;
+    if ((P1.flags & MODES_EVAL_GATE_OK) && !unconditionally_good(P1)) {
+        P1.flags |= MODES_EVAL_P2_VALID;
+        if (at_buffer_start) {                           // j == 0: retried without correction (:1660)
+            P2 = P1;
+            P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
+        } else {
+            uint32_t G[4];
+            frame_order(W.GP2, L.fwd, Gp);
+            frame_order(W.LP2, L.fwd, Lp);
+            D[0] = Gp[0] | Lp[0] | 1u; D[1] = Gp[1] | Lp[1]; D[2] = Gp[2] | Lp[2]; D[3] = Gp[3] | Lp[3];
+#pragma unroll
+            for (int j = 0; j < 4; j++) O[j] = L.fwd ? Gp[j] : Lp[j];
+            O[0] = (O[0] & ~1u) | one0_retry;
+            fill_copies(D, O, G);
+            if (tri2) spread_tie_mask(D, G);
+            if (G[0] == F[0] && G[1] == F[1] && G[2] == F[2] && G[3] == F[3] && tri2 == tri1) {
+                P2 = P1;                                 // same bits, same (uncorrected) delta sums: same verdict
+                P2.flags &= ~(uint32_t)MODES_EVAL_P2_VALID;
+            } else {
+                judge_sliced(G, tri2, d56, d112, fix_errors, aggressive, tab, P2);
+            }
+        }
+    }
+    eval_words(P1, rec);
+    eval_words(P2, rec + 6);
+}
+
+// Evaluate one candidate.  slots: its kSlots words in walk order (not modified); L: phase_setup's
+// result for it; rec: the 12 words of pass[0] and pass[1] of its modes_candidate.
+MODES_SERIAL_FN void evaluate(const uint32_t *slots, const Lane &L, bool at_buffer_start, int fix_errors, int aggressive,
+                              const Tables &tab, Lut lut, uint32_t rec[12]) {
+    Walk W;
+    walk_begin(W, L, slots[0]);
+    walk_blocks(W, L, slots, 0, kBlocks, lut);
+    walk_finish(W, L, at_buffer_start, fix_errors, aggressive, tab, rec);
+}
+
+}  // namespace fused
+
 }  // namespace serial
 }  // namespace modes

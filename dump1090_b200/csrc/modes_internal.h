@@ -64,6 +64,9 @@ void launch_scan(const BatchView &in, const DeviceTables &tab, const ScanOutputs
 void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan,
                  modes_candidate *records, int fix_errors, int aggressive, int sm_count,
                  cudaStream_t stream);
+// The single-walk frame evaluation (modes_eval_fused.cu); parts = 1: whole windows staged, 2: half windows.
+void launch_eval_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
+                       int fix_errors, int aggressive, int sm_count, int parts, cudaStream_t stream);
 void launch_magnitude(const uint8_t *d_iq, uint16_t *d_mag, uint64_t n_samples, const uint16_t *lutn,
                       cudaStream_t stream);
 // CRC / fix on raw frame bytes (hex door): n frames of 14 bytes -> n modes_frame_eval.

@@ -49,7 +49,15 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
         }
         const uint64_t t = (uint64_t)v - 2;
         uint32_t rec[12];
-        if (lean) evaluate<true>(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
+        if (lean == 2) {
+            // the fused single sweep: direction and factors from the preamble words, then the
+            // window in walk order (the kernel stages a backwards walk's words reversed)
+            fused::Lane L;
+            fused::phase_setup(win, odd, tab.lut_iq, 1u, 0xffffffffu, (uint32_t)-16384, L);
+            uint32_t slots[fused::kSlots];
+            for (int u = 0; u < fused::kSlots; u++) slots[u] = L.fwd ? win[8 + u] : win[120 - u];
+            fused::evaluate(slots, L, (t & 131071u) == 0, fix_errors, aggressive, tab, fused::Lut{tab.lut_iq}, rec);
+        } else if (lean) evaluate<true>(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
         else evaluate<false>(win, odd, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
         std::memset(&out[c], 0, sizeof(out[c]));
         out[c].t = (int64_t)t;

@@ -55,7 +55,7 @@ def _evaluate(shim, data, fix, aggressive, lean):
 
 @pytest.mark.parametrize("name", list(STREAMS))
 @pytest.mark.parametrize("fix,aggressive", [(1, 0), (1, 1), (0, 0)])
-@pytest.mark.parametrize("lean", [0, 1], ids=["default", "lean"])
+@pytest.mark.parametrize("lean", [0, 1, 2], ids=["default", "lean", "fused"])
 def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
     got, want = _evaluate(shim, STREAMS[name], fix, aggressive, lean)
     assert want.shape[0] > (200 if name != "retry_at_j0" else 10)
@@ -63,7 +63,7 @@ def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
     assert bad.size == 0, f"{bad.size} of {want.shape[0]} records differ, first at {bad[0]}: {got[bad[0]].tolist()} != {want[bad[0]].tolist()}"
 
 
-@pytest.mark.parametrize("lean", [0, 1], ids=["default", "lean"])
+@pytest.mark.parametrize("lean", [0, 1, 2], ids=["default", "lean", "fused"])
 def test_serial_evaluation_random_alphabets(lean, shim):
     """Many small streams with random amplitude alphabets, preamble jitter and noise levels: weak
     and saturated pairs, long indefinite runs, every gate outcome."""

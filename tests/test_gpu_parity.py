@@ -13,8 +13,9 @@ FLAG_SETS = [dict(), dict(aggressive=1), dict(fix=0), dict(check_crc=0), dict(ch
 
 import streams as S
 
-# all three frame-evaluation kernels: thread per candidate (two codings of the per-bit loops) and warp per candidate
-EVAL_VARIANTS = ["serial", "warp", "lean"]
+# all frame-evaluation kernels: thread per candidate with both attempts in one walk (whole or half
+# windows staged), thread per candidate with two passes (two codings of the per-bit loops), warp per candidate
+EVAL_VARIANTS = ["serial", "warp", "lean", "fused", "fused2"]
 
 
 def _dec_kw(kw):
