@@ -38,15 +38,20 @@ constexpr int kTableWords = 112 + kFixHashSlots + kNibWords + kLutWords;
 static_assert(serial::kIqLutStride == kLutIqStride && serial::kIqLutEntries % 8 == 0, "table geometry");
 static_assert(kTableWords % 2 == 0, "record staging uses 8-byte stores");
 
-template <int kParts> struct Geom {
-    static constexpr int kPart0 = kParts == 1 ? serial::fused::kSlots : 57;          // slots staged first
-    static constexpr int kRow = kPart0;                                                // 113 or 57 words: odd
-    static constexpr int kWarps = kParts == 1 ? 12 : 20;
+template <int kParts, int kWarpsPerSm> struct Geom {
+    // kParts == 1: the whole walk (113 slots) staged at once.  kParts == 2: two halves of 57 slots into
+    // the same rows, slots 0..56 then 56..112 (slot 56 twice: each half starts with the word its first pair begins in).
+    static constexpr int kPartSlots = kParts == 1 ? serial::fused::kSlots : 57;
+    static constexpr int kPartStep = kParts == 1 ? 0 : 56;                            // first slot of part h = h * kPartStep
+    static constexpr int kRow = kPartSlots;                                            // 113 or 57 words: odd
+    static constexpr int kWarps = kWarpsPerSm;
     static constexpr int kThreads = 32 * kWarps;
     static constexpr int kWarpWords = 32 * kRow + 32 * kPreStride;
     static constexpr int kSmemBytes = 4 * (kTableWords + kWarps * kWarpWords);
     static_assert(kRow % 2 == 1 && 32 * kRow >= 32 * 14 && (32 * kRow) % 2 == 0 && kWarpWords % 2 == 0, "row geometry");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory");
+    static_assert(kParts == 1 || (kParts == 2 && kPartStep + kPartSlots == serial::fused::kSlots && serial::fused::kBlockBits * 2 == kPartStep),
+                  "half-window geometry");
 };
 
 __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
@@ -56,6 +61,15 @@ __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) 
 
 __device__ __forceinline__ void cp_async4(uint32_t dst_shared, const uint32_t *src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+
+// One lane's atomic add, as written: the compiler's own form of `if (lane == 0) atomicAdd(...)`
+// aggregates over the active lanes and shuffles the result out right away, which waits for the
+// atomic's round trip at the top of every chunk.
+__device__ __forceinline__ uint32_t atom_add(uint32_t *p, uint32_t x) {
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
+    return old;
 }
 
 // Word w (0..120) of the window of the candidate at virtual position v, whatever it overlaps.
@@ -78,33 +92,41 @@ __device__ __forceinline__ void prestage(const BatchView &in, const uint32_t *bo
     }
 }
 
-// Slots [u0, u0 + count) of all 32 rows of a chunk -> shared memory (row c at rows + c * kRow,
+// Slots [u0, u0 + kCount) of all 32 rows of a chunk -> shared memory (row c at rows + c * kRow,
 // slot u at word u - u0).  Forwards slot u = window word 8 + u, backwards = window word 120 - u.
-template <int kRow>
-__device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *body32, uint32_t my_v, uint32_t rev_mask, bool fast,
-                                           uint32_t *rows, uint32_t rows_s, int u0, int count, int lane) {
+// `w0` = this lane's candidate's first window word as an index into the body's 32-bit words.
+// Branch-free: a backwards row is copied by the mirrored lane assignment (lane l takes slots
+// kCount-1-l, kCount-1-l-32, ...), so that in both directions a lane's source words are 32 apart
+// ascending (compile-time offsets) and only the shared-memory side differs (a select per copy).
+template <int kRow, int kCount>
+__device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *body32, uint32_t my_v, uint32_t w0, uint32_t rev_mask,
+                                           bool fast, uint32_t *rows, uint32_t rows_s, int u0, int lane) {
     if (fast) {
         // common case (no window in the carry block): asynchronous copies straight into shared
         // memory, all 32 rows in flight, one wait (the caller's)
+        constexpr int kCopies = (kCount + 31) / 32;
+        const uint32_t a_fwd = (uint32_t)(8 + u0 + lane), a_rev = (uint32_t)(121 - u0 - kCount + lane);
+        uint32_t d_fwd[kCopies], d_rev[kCopies];
+#pragma unroll
+        for (int j = 0; j < kCopies; j++) {
+            d_fwd[j] = rows_s + 4u * (uint32_t)(lane + 32 * j);
+            d_rev[j] = rows_s + 4u * (uint32_t)(kCount - 1 - lane - 32 * j);
+        }
 #pragma unroll 4
         for (int c = 0; c < 32; c++) {
-            const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
+            const uint32_t w = __shfl_sync(0xffffffffu, w0, c);
             const bool rev = (rev_mask >> c) & 1u;
-            const uint32_t *wp = body32 + ((v - 1 - kHaloSamples) >> 1);
-            // word of slot u0 + lane, and the step to the word of slot u0 + lane + 32
-            const uint32_t *src = rev ? wp + (120 - u0 - lane) : wp + (8 + u0 + lane);
-            const int step = rev ? -32 : 32;
-            const uint32_t dst = rows_s + 4u * (uint32_t)(c * kRow + lane);
-            cp_async4(dst, src);
-            if (lane + 32 < count) cp_async4(dst + 128u, src + step);
-            if (count > 64 && lane + 64 < count) cp_async4(dst + 256u, src + 2 * step);
-            if (count > 96 && lane + 96 < count) cp_async4(dst + 384u, src + 3 * step);
+            const uint32_t *src = body32 + (w + (rev ? a_rev : a_fwd));
+#pragma unroll
+            for (int j = 0; j < kCopies; j++)
+                if (32 * j + 31 < kCount || lane + 32 * j < kCount)
+                    cp_async4((rev ? d_rev[j] : d_fwd[j]) + 4u * (uint32_t)(c * kRow), src + 32 * j);
         }
     } else {
         for (int c = 0; c < 32; c++) {
             const uint32_t v = __shfl_sync(0xffffffffu, my_v, c);
             const bool rev = (rev_mask >> c) & 1u;
-            for (int k = lane; k < count; k += 32) {
+            for (int k = lane; k < kCount; k += 32) {
                 const int u = u0 + k;
                 rows[c * kRow + k] = window_word_slow(in.body, in.halo, in.n_samples, v, rev ? 120 - u : 8 + u);
             }
@@ -112,12 +134,12 @@ __device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *
     }
 }
 
-template <int kParts>
-__global__ void __launch_bounds__(Geom<kParts>::kThreads, 1)
+template <int kParts, int kWarpsPerSm>
+__global__ void __launch_bounds__(Geom<kParts, kWarpsPerSm>::kThreads, 1)
 eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
                   uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive, uint32_t c_one,
                   uint32_t c_m1, uint32_t c_m16k) {
-    using G = Geom<kParts>;
+    using G = Geom<kParts, kWarpsPerSm>;
     namespace fz = serial::fused;
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_nib = s_hash + kFixHashSlots;
@@ -144,11 +166,12 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     const uint32_t total_warps = gridDim.x * G::kWarps;
     const uint32_t *body32 = reinterpret_cast<const uint32_t *>(in.body);
 
+    // Chunks of 32 candidates are handed out from a global counter, requested TWO chunks ahead.
     // (The counter values are used untouched until a chunk later: arithmetic on them right away
     // would wait for the atomic's round trip.)
     uint32_t chunk = blockIdx.x * G::kWarps + warp;
     uint32_t next1 = 0, ahead_raw = 0;
-    if (lane == 0) next1 = atomicAdd(&counters[3], 1u);
+    if (lane == 0) next1 = atom_add(&counters[3], 1u);
     next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
     uint32_t my_v = 0;
     if (chunk < n_chunks) {
@@ -158,7 +181,7 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     while (chunk < n_chunks) {
-        if (lane == 0) ahead_raw = atomicAdd(&counters[3], 1u);
+        if (lane == 0) ahead_raw = atom_add(&counters[3], 1u);
         const uint32_t base = chunk * 32;
         const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;   // idle lanes of the last chunk duplicate its last candidate
         uint32_t v_next = 0;
@@ -169,39 +192,37 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
         fz::phase_setup(pre, odd, s_lut, c_one, c_m1, c_m16k, L);
         const uint32_t rev_mask = __ballot_sync(0xffffffffu, L.fwd == 0u);
         const bool fast = __all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples);
-
-        stage_part<G::kRow>(in, body32, my_v, rev_mask, fast, rows, rows_s, 0, G::kPart0, lane);
-        if (next1 < n_chunks) {                            // the next chunk's positions: loaded behind the copies, used a chunk later
-            const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
-            v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        __syncwarp();
-        if (next1 < n_chunks) {
-            // the next chunk: preamble words on their way behind this chunk's evaluation, windows -> L2
-            // (484 bytes from a 4-byte aligned address: five 128-byte lines)
-            prestage(in, body32, v_next, pre, pre_s);
-            if (v_next > (uint32_t)kHaloSamples) {
-                const uint8_t *wp = in.body + 4ull * ((v_next - 1 - kHaloSamples) >> 1);
-                if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
-#pragma unroll
-                    for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
-                }
-            }
-        }
-
+        const uint32_t w0 = (my_v - 1 - kHaloSamples) >> 1;     // (meaningless for a window in the carry block: slow path)
         const uint32_t *row = rows + lane * G::kRow;
         fz::Walk W;
-        fz::walk_begin(W, L, row[0]);
-        if constexpr (kParts == 1) {
-            fz::walk_blocks(W, L, row, 0, fz::kBlocks, lut);
-        } else {
-            fz::walk_blocks(W, L, row, 0, 2, lut);
-            __syncwarp();                                  // every lane is done with the first half
-            stage_part<G::kRow>(in, body32, my_v, rev_mask, fast, rows, rows_s, G::kPart0, fz::kSlots - G::kPart0, lane);
+
+#pragma unroll 1
+        for (int h = 0; h < kParts; h++) {
+            if (h) __syncwarp();                           // every lane is done with the previous part
+            stage_part<G::kRow, G::kPartSlots>(in, body32, my_v, w0, rev_mask, fast, rows, rows_s, h * G::kPartStep, lane);
+            if (h == 0 && next1 < n_chunks) {              // the next chunk's positions: loaded behind the copies, used a chunk later
+                const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
+                v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
+            }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            fz::walk_blocks(W, L, row - G::kPart0, 2, fz::kBlocks, lut);
+            if (h == 0) {
+                if (next1 < n_chunks) {
+                    // the next chunk: preamble words on their way behind this chunk's evaluation, windows -> L2
+                    // (484 bytes from a 4-byte aligned address: five 128-byte lines)
+                    prestage(in, body32, v_next, pre, pre_s);
+                    if (v_next > (uint32_t)kHaloSamples) {
+                        const uint8_t *wp = in.body + 4ull * ((v_next - 1 - kHaloSamples) >> 1);
+                        if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
+#pragma unroll
+                            for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
+                        }
+                    }
+                }
+                fz::walk_begin(W, L, row[0]);
+            }
+            // part h holds slots h * kPartStep ..: the walk indexes slots from 0
+            fz::walk_blocks(W, L, row - h * G::kPartStep, h * (fz::kBlocks / kParts), (h + 1) * (fz::kBlocks / kParts), lut);
         }
         uint32_t rec[14];
         const uint64_t t = (uint64_t)my_v - 2;
@@ -223,18 +244,18 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     }
 }
 
-template <int kParts>
+template <int kParts, int kWarpsPerSm>
 void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
                   int fix_errors, int aggressive, int sm_count, cudaStream_t stream) {
-    using G = Geom<kParts>;
+    using G = Geom<kParts, kWarpsPerSm>;
     // the opt-in to > 48 KB of dynamic shared memory is per device
     static bool configured[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(eval_fused_kernel<kParts>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+        cudaFuncSetAttribute(eval_fused_kernel<kParts, kWarpsPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    eval_fused_kernel<kParts><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
+    eval_fused_kernel<kParts, kWarpsPerSm><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
                                                                                records, fix_errors, aggressive, 1u, 0xffffffffu, (uint32_t)-16384);
 }
 
@@ -242,8 +263,9 @@ void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutput
 
 void launch_eval_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
                        int fix_errors, int aggressive, int sm_count, int parts, cudaStream_t stream) {
-    if (parts == 2) launch_fused<2>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
-    else launch_fused<1>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    if (parts == 2) launch_fused<2, 20>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    else if (parts == 3) launch_fused<2, 16>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    else launch_fused<1, 12>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
 }
 
 }  // namespace modes

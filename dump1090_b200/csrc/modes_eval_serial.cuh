@@ -156,9 +156,13 @@ MODES_SERIAL_FN void crc_and_fix(uint32_t F[4], int msgbits, uint32_t msgtype, i
     const int off = 112 - msgbits;                      // a short frame uses the last 56 table positions
     const uint32_t W[4] = {bitrev(F[0]), bitrev(F[1]), bitrev(F[2]), bitrev(F[3])};
     uint32_t S = 0;
+    const uint32_t *first14 = tab.nib_syn + (off >> 2) * 16;       // a short frame uses table nibbles 14..27
 #pragma unroll
-    for (int i = 0; i < 28; i++)
-        if (i < 14 || msgbits == 112) S ^= tab.nib_syn[(i + (off >> 2)) * 16 + frame_nibble(W, i)];
+    for (int i = 0; i < 14; i++) S ^= first14[i * 16 + frame_nibble(W, i)];
+    if (msgbits == 112) {                               // one branch, not one per nibble
+#pragma unroll
+        for (int i = 14; i < 28; i++) S ^= tab.nib_syn[i * 16 + frame_nibble(W, i)];
+    }
     errorbit = 0xFF; nfixed = 0;
     if (S != 0 && fix_errors && (msgtype == 11 || msgtype == 17 || msgtype == 18)) {
         const int pmin = off > 5 ? off : 5;             // table positions 5..111 (dump1090.c:806)

@@ -595,7 +595,7 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
 static int eval_variant() {
     const char *e = std::getenv("MODES_EVAL_VARIANT");
     if (!e) return 2;
-    if (e[0] == 'f') return e[5] == '2' ? 4 : 3;          // "fused" / "fused2": the single-walk kernel (modes_eval_fused.cu)
+    if (e[0] == 'f') return e[5] == '2' ? (e[6] == 'b' ? 5 : 4) : 3;   // "fused" / "fused2" / "fused2b": the single-walk kernel (modes_eval_fused.cu)
     return e[0] == 'w' ? 1 : (e[0] == 's' ? 0 : 2);
 }
 
@@ -618,7 +618,7 @@ void launch_eval(const BatchView &in, const DeviceTables &tab, const ScanOutputs
                  cudaStream_t stream) {
     const int variant = eval_variant();
     if (variant >= 3)
-        launch_eval_fused(in, tab, scan, records, fix_errors, aggressive, sm_count, variant == 4 ? 2 : 1, stream);
+        launch_eval_fused(in, tab, scan, records, fix_errors, aggressive, sm_count, variant - 2, stream);
     else if (variant == 1)
         eval_kernel<<<sm_count * 4, kEvalThreads, 0, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
                                                               records, fix_errors, aggressive);
