@@ -166,81 +166,98 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     const uint32_t total_warps = gridDim.x * G::kWarps;
     const uint32_t *body32 = reinterpret_cast<const uint32_t *>(in.body);
 
-    // Chunks of 32 candidates are handed out from a global counter, requested TWO chunks ahead.
+    // Chunks of 32 candidates are handed out from a global counter, requested three chunks ahead:
+    // while chunk i is evaluated, chunk i+1's first part is staged (behind the verdicts of chunk i),
+    // chunk i+2's positions are loaded, its preamble words copied and its windows prefetched into L2.
     // (The counter values are used untouched until a chunk later: arithmetic on them right away
     // would wait for the atomic's round trip.)
-    uint32_t chunk = blockIdx.x * G::kWarps + warp;
-    uint32_t next1 = 0, ahead_raw = 0;
-    if (lane == 0) next1 = atom_add(&counters[3], 1u);
-    next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
-    uint32_t my_v = 0;
-    if (chunk < n_chunks) {
-        const uint32_t n0 = n_cand - chunk * 32 < 32u ? n_cand - chunk * 32 : 32u;
-        my_v = cand_v[chunk * 32 + ((uint32_t)lane < n0 ? lane : n0 - 1)];
-        prestage(in, body32, my_v, pre, pre_s);
-        asm volatile("cp.async.wait_all;" ::: "memory");
-    }
-    while (chunk < n_chunks) {
-        if (lane == 0) ahead_raw = atom_add(&counters[3], 1u);
-        const uint32_t base = chunk * 32;
-        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;   // idle lanes of the last chunk duplicate its last candidate
-        uint32_t v_next = 0;
-
-        // this lane's walk: direction, factors, byte selector (its preamble words arrived a chunk ago)
-        const uint32_t odd = my_v > (uint32_t)kHaloSamples ? ((my_v - 1 - kHaloSamples) & 1u) : 0u;
-        fz::Lane L;
+    auto positions = [&](uint32_t c) -> uint32_t {
+        if (c >= n_chunks) return 0u;
+        const uint32_t nc = n_cand - c * 32 < 32u ? n_cand - c * 32 : 32u;   // idle lanes of the last chunk duplicate its last candidate
+        return cand_v[c * 32 + ((uint32_t)lane < nc ? lane : nc - 1)];
+    };
+    auto look_ahead = [&](uint32_t c, uint32_t v) {      // chunk c (positions v): preamble words -> preamble area, windows -> L2
+        if (c >= n_chunks) return;
+        prestage(in, body32, v, pre, pre_s);
+        if (v > (uint32_t)kHaloSamples) {
+            // 484 bytes from a 4-byte aligned address: five 128-byte lines
+            const uint8_t *wp = in.body + 4ull * ((v - 1 - kHaloSamples) >> 1);
+            if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
+#pragma unroll
+                for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
+            }
+        }
+    };
+    // this lane's walk of the chunk whose preamble words are in the preamble area, and the chunk's first part on its way
+    auto setup_and_stage = [&](uint32_t v, fz::Lane &L, uint32_t &rev_mask, bool &fast) {
+        const uint32_t odd = v > (uint32_t)kHaloSamples ? ((v - 1 - kHaloSamples) & 1u) : 0u;
         fz::phase_setup(pre, odd, s_lut, c_one, c_m1, c_m16k, L);
-        const uint32_t rev_mask = __ballot_sync(0xffffffffu, L.fwd == 0u);
-        const bool fast = __all_sync(0xffffffffu, my_v > (uint32_t)kHaloSamples);
-        const uint32_t w0 = (my_v - 1 - kHaloSamples) >> 1;     // (meaningless for a window in the carry block: slow path)
+        rev_mask = __ballot_sync(0xffffffffu, L.fwd == 0u);
+        fast = __all_sync(0xffffffffu, v > (uint32_t)kHaloSamples);
+        stage_part<G::kRow, G::kPartSlots>(in, body32, v, (v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s, 0, lane);
+    };
+
+    uint32_t chunk = blockIdx.x * G::kWarps + warp;
+    if (chunk >= n_chunks) return;
+    uint32_t next1 = 0, next2_raw = 0;
+    if (lane == 0) { next1 = atom_add(&counters[3], 1u); next2_raw = atom_add(&counters[3], 1u); }
+    next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
+    uint32_t my_v = positions(chunk), v1 = positions(next1);
+    fz::Lane L;
+    uint32_t rev_mask;
+    bool fast;
+    prestage(in, body32, my_v, pre, pre_s);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    setup_and_stage(my_v, L, rev_mask, fast);
+    look_ahead(next1, v1);                                 // (the preamble area is free again: phase_setup has read it)
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    while (true) {
+        // rows: part 0 of `chunk` (complete); L, rev_mask, fast: its walk; preamble area: chunk next1's words (arriving)
+        const uint32_t next2 = total_warps + __shfl_sync(0xffffffffu, next2_raw, 0);
+        if (lane == 0) next2_raw = atom_add(&counters[3], 1u);
+        const uint32_t v2 = positions(next2);              // used after the walk
+        const uint32_t base = chunk * 32;
+        const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;
         const uint32_t *row = rows + lane * G::kRow;
         fz::Walk W;
-
+        fz::walk_begin(W, L, row[0]);
+        fz::walk_blocks(W, L, row, 0, fz::kBlocks / kParts, lut);
 #pragma unroll 1
-        for (int h = 0; h < kParts; h++) {
-            if (h) __syncwarp();                           // every lane is done with the previous part
-            stage_part<G::kRow, G::kPartSlots>(in, body32, my_v, w0, rev_mask, fast, rows, rows_s, h * G::kPartStep, lane);
-            if (h == 0 && next1 < n_chunks) {              // the next chunk's positions: loaded behind the copies, used a chunk later
-                const uint32_t n1 = n_cand - next1 * 32 < 32u ? n_cand - next1 * 32 : 32u;
-                v_next = cand_v[next1 * 32 + ((uint32_t)lane < n1 ? lane : n1 - 1)];
-            }
+        for (int h = 1; h < kParts; h++) {
+            __syncwarp();                                  // every lane is done with the previous part
+            stage_part<G::kRow, G::kPartSlots>(in, body32, my_v, (my_v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s,
+                                              h * G::kPartStep, lane);
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
-            if (h == 0) {
-                if (next1 < n_chunks) {
-                    // the next chunk: preamble words on their way behind this chunk's evaluation, windows -> L2
-                    // (484 bytes from a 4-byte aligned address: five 128-byte lines)
-                    prestage(in, body32, v_next, pre, pre_s);
-                    if (v_next > (uint32_t)kHaloSamples) {
-                        const uint8_t *wp = in.body + 4ull * ((v_next - 1 - kHaloSamples) >> 1);
-                        if ((uint64_t)(wp - in.body) + 640u <= 2ull * in.n_samples) {
-#pragma unroll
-                            for (int k = 0; k < 5; k++) asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + 128 * k));
-                        }
-                    }
-                }
-                fz::walk_begin(W, L, row[0]);
-            }
             // part h holds slots h * kPartStep ..: the walk indexes slots from 0
             fz::walk_blocks(W, L, row - h * G::kPartStep, h * (fz::kBlocks / kParts), (h + 1) * (fz::kBlocks / kParts), lut);
         }
-        uint32_t rec[14];
+        __syncwarp();                                      // the rows are free
         const uint64_t t = (uint64_t)my_v - 2;
-        rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
-        fz::walk_finish(W, L, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive, T, rec + 2);
-        __syncwarp();
-        if ((uint32_t)lane < n) {
-#pragma unroll
-            for (int k = 0; k < 14; k += 2) *reinterpret_cast<uint2 *>(rows + 14 * lane + k) = make_uint2(rec[k], rec[k + 1]);
+        const fz::Lane Lcur = L;
+        const bool more = next1 < n_chunks;
+        if (more) {
+            // the next chunk's first part is copied while this chunk's verdicts are worked out
+            asm volatile("cp.async.wait_all;" ::: "memory");   // its preamble words (issued a walk ago)
+            setup_and_stage(v1, L, rev_mask, fast);
+            look_ahead(next2, v2);
         }
+        uint32_t rec[14];
+        rec[0] = (uint32_t)t; rec[1] = (uint32_t)(t >> 32);
+        fz::walk_finish(W, Lcur, (((uint32_t)t) & (kBufSamples - 1)) == 0, fix_errors, aggressive, T, rec + 2);
+        if ((uint32_t)lane < n) {
+            // 56-byte records, 8-byte aligned: straight from registers (the rows are being overwritten)
+            uint2 *dst = reinterpret_cast<uint2 *>(records + base + lane);
+#pragma unroll
+            for (int k = 0; k < 7; k++) dst[k] = make_uint2(rec[2 * k], rec[2 * k + 1]);
+        }
+        if (!more) break;
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncwarp();
-        uint32_t *dst = reinterpret_cast<uint32_t *>(records + base);
-        for (uint32_t i = lane; i < n * 14; i += 32) dst[i] = rows[i];
-        asm volatile("cp.async.wait_all;" ::: "memory");   // the next chunk's preamble words
-        __syncwarp();
-        chunk = next1;
-        my_v = v_next;
-        next1 = total_warps + __shfl_sync(0xffffffffu, ahead_raw, 0);
+        chunk = next1; next1 = next2;
+        my_v = v1; v1 = v2;
     }
 }
 

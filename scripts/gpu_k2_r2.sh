@@ -5,4 +5,4 @@ tag=${1:-k2}
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fused" 2>&1 | tail -8 ) > gpurun_out/r2${tag}_pytest.log; tail -3 gpurun_out/r2${tag}_pytest.log
 bash scripts/gpu_exp.sh ${tag} < scripts/exp_list.txt
-[ -n "$2" ] && bash scripts/gpu_ncu_k2.sh $2
+if [ -n "$2" ]; then bash scripts/gpu_ncu_k2.sh $2; fi
