@@ -15,12 +15,15 @@
 //    reversed (the copy is a 4-byte cp.async per word anyway: windows are only 4-byte aligned).
 //    Every lane then reads ascending slots at compile-time offsets; row stride odd: lane l's slot
 //    k sits in bank (stride*l + k) mod 32, conflict free whatever the directions are.
-//  * kParts == 2 stages half a window at a time into the same rows (first 57 slots, then the other
-//    56): 8.4 KB per warp instead of 15.6, 20 warps per SM instead of 12.  The second half's copy
-//    is exposed (it cannot start before all lanes finished the first half) but hits L2 (the
-//    windows were prefetched a chunk earlier) and the other warps of the scheduler cover it.
-//  * Chunks of 32 candidates are handed out from a global counter two ahead, the next chunk's
-//    positions are loaded behind the copies and its windows prefetched into L2, as before.
+//  * The next chunk's windows are copied while the current chunk's verdicts (mask assembly, CRC,
+//    repair) are worked out: the rows are free as soon as every lane has finished its walk, and
+//    the verdicts leave straight from registers.  Chunks of 32 candidates are handed out from a
+//    global counter three ahead: chunk i+2's positions are loaded, its preamble words copied and
+//    its windows prefetched into L2 while chunk i is walked.
+//  * MODES_EVAL_VARIANT=fused2 stages half a window at a time into the same rows (57 slots, then
+//    the other 57, slot 56 twice): 8.4 KB per warp instead of 15.6, 16 warps per SM instead of 12.
+//    The second half's copy is exposed (it cannot start before all lanes finished the first half);
+//    measured slightly slower than whole windows (0.170 against 0.166 ms).
 #include <cstdint>
 #include <cstdlib>
 #include <cuda_runtime.h>
@@ -38,20 +41,22 @@ constexpr int kTableWords = 112 + kFixHashSlots + kNibWords + kLutWords;
 static_assert(serial::kIqLutStride == kLutIqStride && serial::kIqLutEntries % 8 == 0, "table geometry");
 static_assert(kTableWords % 2 == 0, "record staging uses 8-byte stores");
 
-template <int kParts, int kWarpsPerSm> struct Geom {
-    // kParts == 1: the whole walk (113 slots) staged at once.  kParts == 2: two halves of 57 slots into
-    // the same rows, slots 0..56 then 56..112 (slot 56 twice: each half starts with the word its first pair begins in).
-    static constexpr int kPartSlots = kParts == 1 ? serial::fused::kSlots : 57;
-    static constexpr int kPartStep = kParts == 1 ? 0 : 56;                            // first slot of part h = h * kPartStep
-    static constexpr int kRow = kPartSlots;                                            // 113 or 57 words: odd
+// kFirst = blocks of the walk (of 4) whose slots are staged first; the rest follows into the same
+// rows once every lane is through them.  4: the whole walk (113 slots) at once, 12 warps per SM;
+// 3: 85 slots, then 29 (16 warps); 2: two halves of 57 (slot 56 twice: a part starts with the word
+// its first pair begins in).
+template <int kFirst, int kWarpsPerSm> struct Geom {
+    static constexpr int kParts = kFirst == serial::fused::kBlocks ? 1 : 2;
+    static constexpr int kSlots0 = serial::fused::kBlockBits * kFirst + 1;                              // slots of part 0
+    static constexpr int kSlots1 = serial::fused::kBlockBits * (serial::fused::kBlocks - kFirst) + 1;   // slots of part 1 (from slot 28 * kFirst)
+    static constexpr int kRow = kSlots0 > kSlots1 ? kSlots0 : kSlots1;                                  // 113, 85 or 57 words: odd
     static constexpr int kWarps = kWarpsPerSm;
     static constexpr int kThreads = 32 * kWarps;
     static constexpr int kWarpWords = 32 * kRow + 32 * kPreStride;
     static constexpr int kSmemBytes = 4 * (kTableWords + kWarps * kWarpWords);
-    static_assert(kRow % 2 == 1 && 32 * kRow >= 32 * 14 && (32 * kRow) % 2 == 0 && kWarpWords % 2 == 0, "row geometry");
+    static_assert(kFirst >= 2 && kFirst <= serial::fused::kBlocks, "split");
+    static_assert(kRow % 2 == 1 && (32 * kRow) % 2 == 0 && kWarpWords % 2 == 0, "row geometry");
     static_assert(kSmemBytes <= 227 * 1024, "shared memory");
-    static_assert(kParts == 1 || (kParts == 2 && kPartStep + kPartSlots == serial::fused::kSlots && serial::fused::kBlockBits * 2 == kPartStep),
-                  "half-window geometry");
 };
 
 __device__ __forceinline__ uint32_t raw_sample(const BatchView &in, uint64_t v) {
@@ -134,12 +139,12 @@ __device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *
     }
 }
 
-template <int kParts, int kWarpsPerSm>
-__global__ void __launch_bounds__(Geom<kParts, kWarpsPerSm>::kThreads, 1)
+template <int kFirst, int kWarpsPerSm>
+__global__ void __launch_bounds__(Geom<kFirst, kWarpsPerSm>::kThreads, 1)
 eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
                   uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive, uint32_t c_one,
                   uint32_t c_m1, uint32_t c_m16k) {
-    using G = Geom<kParts, kWarpsPerSm>;
+    using G = Geom<kFirst, kWarpsPerSm>;
     namespace fz = serial::fused;
     extern __shared__ __align__(16) uint32_t s_mem[];
     uint32_t *s_syn = s_mem, *s_hash = s_syn + 112, *s_nib = s_hash + kFixHashSlots;
@@ -194,7 +199,7 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
         fz::phase_setup(pre, odd, s_lut, c_one, c_m1, c_m16k, L);
         rev_mask = __ballot_sync(0xffffffffu, L.fwd == 0u);
         fast = __all_sync(0xffffffffu, v > (uint32_t)kHaloSamples);
-        stage_part<G::kRow, G::kPartSlots>(in, body32, v, (v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s, 0, lane);
+        stage_part<G::kRow, G::kSlots0>(in, body32, v, (v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s, 0, lane);
     };
 
     uint32_t chunk = blockIdx.x * G::kWarps + warp;
@@ -223,16 +228,16 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
         const uint32_t *row = rows + lane * G::kRow;
         fz::Walk W;
         fz::walk_begin(W, L, row[0]);
-        fz::walk_blocks(W, L, row, 0, fz::kBlocks / kParts, lut);
+        constexpr int kU1 = fz::kBlockBits * kFirst;       // part 1 holds slots kU1 ..: the walk indexes slots from 0
 #pragma unroll 1
-        for (int h = 1; h < kParts; h++) {
-            __syncwarp();                                  // every lane is done with the previous part
-            stage_part<G::kRow, G::kPartSlots>(in, body32, my_v, (my_v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s,
-                                              h * G::kPartStep, lane);
-            asm volatile("cp.async.wait_all;" ::: "memory");
-            __syncwarp();
-            // part h holds slots h * kPartStep ..: the walk indexes slots from 0
-            fz::walk_blocks(W, L, row - h * G::kPartStep, h * (fz::kBlocks / kParts), (h + 1) * (fz::kBlocks / kParts), lut);
+        for (int h = 0; h < G::kParts; h++) {              // (a loop, so that the walk's code exists once)
+            if (h) {
+                __syncwarp();                              // every lane is done with part 0
+                stage_part<G::kRow, G::kSlots1>(in, body32, my_v, (my_v - 1 - kHaloSamples) >> 1, rev_mask, fast, rows, rows_s, kU1, lane);
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncwarp();
+            }
+            fz::walk_blocks(W, L, h ? row - kU1 : row, h ? kFirst : 0, h ? fz::kBlocks : kFirst, lut);
         }
         __syncwarp();                                      // the rows are free
         const uint64_t t = (uint64_t)my_v - 2;
@@ -261,18 +266,18 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     }
 }
 
-template <int kParts, int kWarpsPerSm>
+template <int kFirst, int kWarpsPerSm>
 void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
                   int fix_errors, int aggressive, int sm_count, cudaStream_t stream) {
-    using G = Geom<kParts, kWarpsPerSm>;
+    using G = Geom<kFirst, kWarpsPerSm>;
     // the opt-in to > 48 KB of dynamic shared memory is per device
     static bool configured[64] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || !configured[dev]) {
-        cudaFuncSetAttribute(eval_fused_kernel<kParts, kWarpsPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+        cudaFuncSetAttribute(eval_fused_kernel<kFirst, kWarpsPerSm>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    eval_fused_kernel<kParts, kWarpsPerSm><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
+    eval_fused_kernel<kFirst, kWarpsPerSm><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
                                                                                records, fix_errors, aggressive, 1u, 0xffffffffu, (uint32_t)-16384);
 }
 
@@ -280,9 +285,10 @@ void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutput
 
 void launch_eval_fused(const BatchView &in, const DeviceTables &tab, const ScanOutputs &scan, modes_candidate *records,
                        int fix_errors, int aggressive, int sm_count, int parts, cudaStream_t stream) {
-    if (parts == 2) launch_fused<2, 20>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
-    else if (parts == 3) launch_fused<2, 16>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
-    else launch_fused<1, 12>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    // measured on the bench's 845 458 candidates: whole windows, 12 warps per SM 0.166 ms; half windows, 16 warps
+    // 0.170 ms (20 warps: 0.195 ms, the register limit spills; 85 + 29 slots, 16 warps: 0.183 ms)
+    if (parts == 2) launch_fused<2, 16>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
+    else launch_fused<4, 12>(in, tab, scan, records, fix_errors, aggressive, sm_count, stream);
 }
 
 }  // namespace modes

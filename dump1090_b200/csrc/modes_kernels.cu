@@ -588,14 +588,15 @@ eval_serial_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ 
     }
 }
 
-// MODES_EVAL_VARIANT: default "lean" = thread per candidate with the leaner per-bit loops (measured
-// 0.269 ms against 0.292 ms for the bench's 845 458 candidates); "serial" = the same kernel with the
-// first coding of the per-bit loops; "warp" = the warp-per-candidate kernel (the first formulation).
-// All three stay in the parity tests.  Read per launch (tests switch it within one process).
+// MODES_EVAL_VARIANT: default "fused" = thread per candidate, both attempts in one walk
+// (modes_eval_fused.cu; measured 0.166 ms for the bench's 845 458 candidates), "fused2" = the same with
+// half windows staged (0.170 ms); "lean" = thread per candidate, two passes (0.242 ms), "serial" = the same
+// kernel with the first coding of the per-bit loops (0.290 ms); "warp" = the warp-per-candidate kernel
+// (the first formulation, 0.56 ms).  All stay in the parity tests.  Read per launch (tests switch it
+// within one process).
 static int eval_variant() {
     const char *e = std::getenv("MODES_EVAL_VARIANT");
-    if (!e) return 2;
-    if (e[0] == 'f') return e[5] == '2' ? (e[6] == 'b' ? 5 : 4) : 3;   // "fused" / "fused2" / "fused2b": the single-walk kernel (modes_eval_fused.cu)
+    if (!e || e[0] == 'f') return (e && e[5] == '2') ? 4 : 3;
     return e[0] == 'w' ? 1 : (e[0] == 's' ? 0 : 2);
 }
 

@@ -14,4 +14,4 @@ dec.kernel_times_ms()
 for _ in range(20):
     dec.detect_device(d.data_ptr(), 4096); n = dec.detect_wait()
 t = dec.kernel_times_ms()
-print(f"eval variant {os.environ.get('MODES_EVAL_VARIANT','lean')}: scan {t[0]:.4f} ms  eval {t[1]:.4f} ms  cands {n}  -> {2*(1<<29)/t[0]/1e6:.0f} GB/s", flush=True)
+print(f"eval variant {os.environ.get('MODES_EVAL_VARIANT','fused')}: scan {t[0]:.4f} ms  eval {t[1]:.4f} ms  cands {n}  -> {2*(1<<29)/t[0]/1e6:.0f} GB/s", flush=True)
