@@ -117,15 +117,24 @@ __device__ __forceinline__ void stage_part(const BatchView &in, const uint32_t *
             d_fwd[j] = rows_s + 4u * (uint32_t)(lane + 32 * j);
             d_rev[j] = rows_s + 4u * (uint32_t)(kCount - 1 - lane - 32 * j);
         }
-#pragma unroll 4
-        for (int c = 0; c < 32; c++) {
-            const uint32_t w = __shfl_sync(0xffffffffu, w0, c);
-            const bool rev = (rev_mask >> c) & 1u;
-            const uint32_t *src = body32 + (w + (rev ? a_rev : a_fwd));
+        // rows in groups of eight: inside a group the row's offset is a compile-time immediate, between
+        // groups the eight shared-memory bases move on
+        uint32_t rm = rev_mask;
+#pragma unroll 1
+        for (int g = 0; g < 32; g += 8) {
 #pragma unroll
-            for (int j = 0; j < kCopies; j++)
-                if (32 * j + 31 < kCount || lane + 32 * j < kCount)
-                    cp_async4((rev ? d_rev[j] : d_fwd[j]) + 4u * (uint32_t)(c * kRow), src + 32 * j);
+            for (int ci = 0; ci < 8; ci++) {
+                const uint32_t w = __shfl_sync(0xffffffffu, w0, g + ci);
+                const bool rev = (rm >> ci) & 1u;
+                const uint32_t *src = body32 + (w + (rev ? a_rev : a_fwd));
+#pragma unroll
+                for (int j = 0; j < kCopies; j++)
+                    if (32 * j + 31 < kCount || lane + 32 * j < kCount)
+                        cp_async4((rev ? d_rev[j] : d_fwd[j]) + 4u * (uint32_t)(ci * kRow), src + 32 * j);
+            }
+            rm >>= 8;
+#pragma unroll
+            for (int j = 0; j < kCopies; j++) { d_fwd[j] += 4u * 8u * (uint32_t)kRow; d_rev[j] += 4u * 8u * (uint32_t)kRow; }
         }
     } else {
         for (int c = 0; c < 32; c++) {

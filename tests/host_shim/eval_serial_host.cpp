@@ -49,7 +49,22 @@ extern "C" int shim_eval_candidates(const uint8_t *virt, uint64_t n_virtual_samp
         }
         const uint64_t t = (uint64_t)v - 2;
         uint32_t rec[12];
-        if (lean == 2) {
+        if (lean == 3) {
+            // the same walk from half windows, as eval_fused_kernel<2, ..> stages them: slots 0..56, then
+            // slots 56..112 into the same 57 words
+            fused::Lane L;
+            fused::phase_setup(win, odd, tab.lut_iq, 1u, 0xffffffffu, (uint32_t)-16384, L);
+            uint32_t part[fused::kSlots];
+            fused::Walk W;
+            for (int u = 0; u < fused::kSlots; u++) part[u] = 0xdeadbeefu;
+            for (int u = 0; u < 57; u++) part[u] = L.fwd ? win[8 + u] : win[120 - u];
+            fused::walk_begin(W, L, part[0]);
+            fused::walk_blocks(W, L, part, 0, 2, fused::Lut{tab.lut_iq});
+            for (int u = 0; u < 56; u++) part[u] = 0xdeadbeefu;         // the second half must not look back
+            for (int u = 56; u < fused::kSlots; u++) part[u] = L.fwd ? win[8 + u] : win[120 - u];
+            fused::walk_blocks(W, L, part, 2, 4, fused::Lut{tab.lut_iq});
+            fused::walk_finish(W, L, (t & 131071u) == 0, fix_errors, aggressive, tab, rec);
+        } else if (lean == 2) {
             // the fused single sweep: direction and factors from the preamble words, then the
             // window in walk order (the kernel stages a backwards walk's words reversed)
             fused::Lane L;

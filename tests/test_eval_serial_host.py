@@ -1,5 +1,6 @@
-"""CPU check of the per-candidate evaluation that eval_serial_kernel runs one thread per candidate
-(dump1090_b200/csrc/modes_eval_serial.cuh): the same header is compiled for the host
+"""CPU check of the per-candidate evaluation that the frame-evaluation kernels run one thread per
+candidate (dump1090_b200/csrc/modes_eval_serial.cuh: the single walk of eval_fused_kernel, whole and
+half windows, and the two-pass codings of eval_serial_kernel): the same header is compiled for the host
 (tests/host_shim/, test infrastructure only) and fed the oracle's candidate positions; the
 evaluated records — both attempts, frame bytes, gate/CRC/repair verdicts — must equal the
 oracle's byte for byte.  The GPU parity tests check the kernel itself."""
@@ -55,7 +56,7 @@ def _evaluate(shim, data, fix, aggressive, lean):
 
 @pytest.mark.parametrize("name", list(STREAMS))
 @pytest.mark.parametrize("fix,aggressive", [(1, 0), (1, 1), (0, 0)])
-@pytest.mark.parametrize("lean", [0, 1, 2], ids=["default", "lean", "fused"])
+@pytest.mark.parametrize("lean", [0, 1, 2, 3], ids=["two_pass", "two_pass_lean", "fused", "fused_halves"])
 def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
     got, want = _evaluate(shim, STREAMS[name], fix, aggressive, lean)
     assert want.shape[0] > (200 if name != "retry_at_j0" else 10)
@@ -63,7 +64,7 @@ def test_serial_evaluation_matches_oracle(name, fix, aggressive, lean, shim):
     assert bad.size == 0, f"{bad.size} of {want.shape[0]} records differ, first at {bad[0]}: {got[bad[0]].tolist()} != {want[bad[0]].tolist()}"
 
 
-@pytest.mark.parametrize("lean", [0, 1, 2], ids=["default", "lean", "fused"])
+@pytest.mark.parametrize("lean", [0, 1, 2, 3], ids=["two_pass", "two_pass_lean", "fused", "fused_halves"])
 def test_serial_evaluation_random_alphabets(lean, shim):
     """Many small streams with random amplitude alphabets, preamble jitter and noise levels: weak
     and saturated pairs, long indefinite runs, every gate outcome."""
