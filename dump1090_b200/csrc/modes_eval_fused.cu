@@ -68,9 +68,12 @@ __device__ __forceinline__ void cp_async4(uint32_t dst_shared, const uint32_t *s
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 
-// One lane's atomic add, as written: the compiler's own form of `if (lane == 0) atomicAdd(...)`
-// aggregates over the active lanes and shuffles the result out right away, which waits for the
-// atomic's round trip at the top of every chunk.
+// One lane's atomic add.  For an atomic on a warp-uniform address in divergent code ptxas emits its
+// aggregated form (leader election, population count, and a shuffle of the result right behind
+// the atomic), and that shuffle waits for the atomic's round trip at the top of every chunk (3.7 %
+// of the kernel).  The hand-out counter is therefore addressed as counters + 3 + lane * c_zero with
+// c_zero = 0 from a kernel parameter: not provably uniform, so the atomic stays a plain one and its
+// result is first touched a chunk later.
 __device__ __forceinline__ uint32_t atom_add(uint32_t *p, uint32_t x) {
     uint32_t old;
     asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(x) : "memory");
@@ -152,7 +155,7 @@ template <int kFirst, int kWarpsPerSm>
 __global__ void __launch_bounds__(Geom<kFirst, kWarpsPerSm>::kThreads, 1)
 eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ cand_v, uint32_t *counters,
                   uint32_t cand_capacity, modes_candidate *records, int fix_errors, int aggressive, uint32_t c_one,
-                  uint32_t c_m1, uint32_t c_m16k) {
+                  uint32_t c_m1, uint32_t c_m16k, uint32_t c_zero) {
     using G = Geom<kFirst, kWarpsPerSm>;
     namespace fz = serial::fused;
     extern __shared__ __align__(16) uint32_t s_mem[];
@@ -214,7 +217,8 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     uint32_t chunk = blockIdx.x * G::kWarps + warp;
     if (chunk >= n_chunks) return;
     uint32_t next1 = 0, next2_raw = 0;
-    if (lane == 0) { next1 = atom_add(&counters[3], 1u); next2_raw = atom_add(&counters[3], 1u); }
+    uint32_t *const hand_out = counters + 3 + lane * c_zero;
+    if (lane == 0) { next1 = atom_add(hand_out, 1u); next2_raw = atom_add(hand_out, 1u); }
     next1 = total_warps + __shfl_sync(0xffffffffu, next1, 0);
     uint32_t my_v = positions(chunk), v1 = positions(next1);
     fz::Lane L;
@@ -230,7 +234,7 @@ eval_fused_kernel(BatchView in, DeviceTables tab, const uint32_t *__restrict__ c
     while (true) {
         // rows: part 0 of `chunk` (complete); L, rev_mask, fast: its walk; preamble area: chunk next1's words (arriving)
         const uint32_t next2 = total_warps + __shfl_sync(0xffffffffu, next2_raw, 0);
-        if (lane == 0) next2_raw = atom_add(&counters[3], 1u);
+        if (lane == 0) next2_raw = atom_add(hand_out, 1u);
         const uint32_t v2 = positions(next2);              // used after the walk
         const uint32_t base = chunk * 32;
         const uint32_t n = n_cand - base < 32u ? n_cand - base : 32u;
@@ -287,7 +291,7 @@ void launch_fused(const BatchView &in, const DeviceTables &tab, const ScanOutput
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     eval_fused_kernel<kFirst, kWarpsPerSm><<<sm_count, G::kThreads, G::kSmemBytes, stream>>>(in, tab, scan.cand_v, scan.counters, scan.cand_capacity,
-                                                                               records, fix_errors, aggressive, 1u, 0xffffffffu, (uint32_t)-16384);
+                                                                               records, fix_errors, aggressive, 1u, 0xffffffffu, (uint32_t)-16384, 0u);
 }
 
 }  // namespace
