@@ -7,7 +7,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS   := $(ARCH) -O3 -lineinfo -std=c++17 -Iinclude -Xcompiler -fPIC,-Wall,-Wextra
 CSRC      := dump1090_b200/csrc
 LIB       := dump1090_b200/libmodes_b200.so
-OBJS      := build/modes_kernels.o build/modes_scan2.o build/modes_eval_fused.o build/modes_resolve_gpu.o build/modes_api.o build/modes_resolve.o build/modes_tables.o build/modes_format.o build/modes_tracker.o
+OBJS      := build/modes_kernels.o build/modes_scan2.o build/modes_eval_fused.o build/modes_resolve_gpu.o build/modes_api.o build/modes_resolve.o build/modes_tables.o build/modes_format.o build/modes_tracker.o build/modes_pool.o
 
 all: $(LIB) dump1090-b200
 

@@ -4,6 +4,7 @@
     python bench.py --gpus N --steps K --warmup W            # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path, all host cores
     python bench.py --workload df17_aggressive|tiled_64g|snr_sweep ...   # BASELINE.json configs[2..4]
+    python bench.py --workload receivers --receivers 256               # many receivers, one GPU
 
 Default workload (BASELINE.json configs[1]): testfiles/modes1.bin tiled back to back to 1 GiB
 (536 870 912 samples = 4096 reference buffers) per GPU, --no-fix.  Weak scaling: rank r holds the
@@ -179,6 +180,9 @@ def run_reference(args) -> None:
     import multiprocessing as mp
     import checker
     name = args.workload
+    if name == "receivers":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference serves one receiver per process: its rate per core is the tiled_nofix figure of this arm (147 Msamples/s = 73 receivers per core)"}))
+        return
     if name == "snr_sweep":
         print(json.dumps({"impl": "reference", "unavailable": "snr_sweep compares detect rates; run --workload snr_sweep on the GPU arm, which times the oracle alongside"}))
         return
@@ -775,13 +779,89 @@ def run_snr_sweep(args) -> None:
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- many receivers
+
+def run_receivers(args) -> None:
+    """Many independent 2 MHz receivers on one GPU (modes_pool_*): every step takes ONE 131072-sample
+    buffer from each of R receivers (pinned host memory in, messages out, per-receiver address caches and
+    carries), i.e. the live-ingest shape of rtlsdrCallback (dump1090.c:442-456) batched across receivers
+    instead of across time.  Receiver r's stream is the tiled capture starting r buffers in; receiver 0's
+    messages are checked against the CPU oracle's decode of its stream."""
+    import ctypes
+    import torch
+    import checker
+    from dump1090_b200 import api
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    torch.cuda.set_device(0)
+    n_rx = max(1, args.receivers)
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    capture, what = load_capture()
+    BUF = api.BUFFER_BYTES
+    total = steps + warm
+    # one pinned block: the tiled capture, long enough that receiver r can read buffers r .. r+total
+    pinned = api.PinnedBuffer((n_rx + total) * BUF)
+    pinned.array[:] = shard_bytes(capture, 0, (n_rx + total) * BUF)
+    ids = np.arange(n_rx, dtype=np.uint32)
+    first = []
+    msgs = 0
+    sampler = ClockSampler(0)
+    with api.ReceiverPool(n_rx, fix_errors=0) as pool:
+        # messages of all receivers land in one array (modes_pool_set_output), receiver 0's are kept for the check
+        out, out_rx = pool.set_output_array(n_rx * 400 + 4096)
+
+        def step(k):
+            ptrs = (ctypes.c_void_p * n_rx)(*[pinned.ptr + (r + k) * BUF for r in range(n_rx)])
+            pool.rearm_output()
+            pool.ingest_ptrs(ids, ptrs)
+            n = pool.output_count()
+            assert n <= len(out), "message array too small"
+            return n
+
+        def keep(n):
+            for j in np.nonzero(out_rx[:n] == 0)[0]:
+                first.append(out[j].raw_line())
+        for k in range(warm):
+            keep(step(k))
+        torch.cuda.synchronize()
+        sampler.start()
+        dt = 0.0
+        for k in range(warm, total):
+            t0 = time.perf_counter()
+            n = step(k)
+            dt += time.perf_counter() - t0
+            msgs += n
+            keep(n)                                     # outside the timed region: the check's bookkeeping
+        clocks = sampler.stop()
+        stats0 = list(pool.stats(0).values())
+    exp, exp_stats = checker.oracle_decode(pinned.array[: total * BUF], fix=0, drop_eof=1, cap=4_000_000)
+    ok = first == [m.hexline() for m in exp] and stats0 == exp_stats
+    samples = n_rx * steps * 131072
+    os.dup2(saved_stdout, 1)
+    print(json.dumps({
+        "metric": METRIC, "value": round(samples / dt / 1e6, 1), "unit": "Msamples/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": round(1e3 * dt / steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": f"synthetic: {what}, receiver r starts r buffers in",
+        "config": {"workload": f"{n_rx} independent receivers, one 131072-sample buffer of each per step through modes_pool_ingest "
+                               "(SURVEY.md 8(f) item 4), --no-fix", "flags": "--no-fix", "receivers": n_rx,
+                   "samples_per_step": n_rx * 131072, "h2d_bytes_per_step": n_rx * (BUF + api.CARRY_BYTES),
+                   "device_bytes_scanned_per_step": 2 * n_rx * BUF,
+                   "step": "carries + buffers H2D, scan + frame evaluation over 2R buffers (pad, data pairs), records D2H, "
+                           "per-receiver host resolve, messages through the sink; wall clock"},
+        "clocks": clocks, "messages_per_step": round(msgs / steps, 1),
+        "receivers_in_real_time": int(samples / dt / 2e6),
+        "parity_checked": bool(ok), "parity": {"receiver_0_equals_oracle_decode_of_its_stream": bool(ok), "messages_receiver_0": len(first)},
+        "note": "value is end to end (host buffers in, messages out); one receiver delivers 2 M samples/s"}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tiled_nofix", choices=list(WORKLOADS) + ["snr_sweep"])
+    ap.add_argument("--workload", default="tiled_nofix", choices=list(WORKLOADS) + ["snr_sweep", "receivers"])
+    ap.add_argument("--receivers", type=int, default=256, help="receivers: independent streams, one buffer of each per step")
     ap.add_argument("--frames", type=int, default=10000, help="snr_sweep: frames per SNR point (whole job)")
     ap.add_argument("--gpu-resolve", type=int, default=0, help="N=1 e2e: 1 = the order-dependent half on the GPU too (modes_config.gpu_resolve)")
     args = ap.parse_args()
@@ -789,6 +869,8 @@ def main():
         run_reference(args)
     elif args.workload == "snr_sweep":
         run_snr_sweep(args)
+    elif args.workload == "receivers":
+        run_receivers(args)
     else:
         run_ours(args)
 

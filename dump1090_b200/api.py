@@ -94,6 +94,7 @@ STAT_NAMES = ["valid_preamble", "out_of_phase", "demodulated", "goodcrc", "badcr
               "single_bit_fix", "two_bits_fix"]
 
 SINK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(Message))
+POOL_SINK_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.POINTER(Message))
 
 CANDIDATE_DTYPE = np.dtype([("t", "<i8"),
                             ("p", [("msg", "u1", 14), ("msgtype", "u1"), ("flags", "u1"), ("errorbit", "u1"),
@@ -115,7 +116,9 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_host_free", "modes_get_kernel_times", "modes_launch_count", "modes_tile_count", "modes_set_host_wait",
            "modes_tracker_create", "modes_tracker_destroy", "modes_tracker_update", "modes_tracker_count",
            "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
-           "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl"]
+           "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl",
+           "modes_pool_create", "modes_pool_destroy", "modes_pool_last_error", "modes_pool_ingest", "modes_pool_resolve",
+           "modes_pool_stats", "modes_pool_reset", "modes_pool_buffers", "modes_pool_set_output", "modes_pool_output_count"]
 
 
 def lib():
@@ -190,6 +193,20 @@ def lib():
         L.modes_resolver_commit.argtypes = [C.c_void_p, SINK_FN, C.c_void_p]
         L.modes_tile_count.restype = C.c_size_t
         L.modes_tile_count.argtypes = [C.c_size_t]
+        L.modes_pool_create.restype = C.c_void_p
+        L.modes_pool_create.argtypes = [C.POINTER(Config), C.c_size_t, C.c_size_t]
+        L.modes_pool_destroy.argtypes = [C.c_void_p]
+        L.modes_pool_last_error.restype = C.c_char_p
+        L.modes_pool_last_error.argtypes = [C.c_void_p]
+        L.modes_pool_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, POOL_SINK_FN, C.c_void_p]
+        L.modes_pool_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, POOL_SINK_FN, C.c_void_p]
+        L.modes_pool_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Stats)]
+        L.modes_pool_reset.argtypes = [C.c_void_p, C.c_uint32]
+        L.modes_pool_set_output.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_pool_output_count.restype = C.c_size_t
+        L.modes_pool_output_count.argtypes = [C.c_void_p]
+        L.modes_pool_buffers.restype = C.c_int64
+        L.modes_pool_buffers.argtypes = [C.c_void_p, C.c_uint32]
         _lib = L
     return _lib
 
@@ -515,6 +532,96 @@ class Resolver:
         if self._h:
             lib().modes_resolver_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- many receivers on one GPU ----------------------------------------
+
+class ReceiverPool:
+    """modes_pool_*: independent 2 MHz streams (one address cache, carry, skip state and set of
+    statistics each, as one dump1090 process keeps per receiver), one buffer of each decoded per
+    batch.  Messages are collected per receiver (`take(receiver)`)."""
+
+    def __init__(self, n_receivers: int, max_batch: int = 0, **cfg):
+        self.cfg = make_config(**cfg)
+        self.n = n_receivers
+        self._h = lib().modes_pool_create(C.byref(self.cfg), n_receivers, max_batch)
+        if not self._h:
+            raise RuntimeError("modes_pool_create failed")
+        self.messages = [[] for _ in range(n_receivers)]
+        self._fn = POOL_SINK_FN(self._on)
+
+    def _on(self, _user, receiver, mm):
+        self.messages[receiver].append(mm.contents.copy())
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(lib().modes_pool_last_error(self._h).decode())
+
+    def ingest(self, receivers, buffers) -> None:
+        """buffers[i]: BUFFER_BYTES of uint8 I/Q (numpy) = the next buffer of receivers[i]."""
+        ids = np.ascontiguousarray(receivers, dtype=np.uint32)
+        bufs = [np.ascontiguousarray(b, dtype=np.uint8) for b in buffers]
+        assert ids.size == len(bufs) and all(b.size == BUFFER_BYTES for b in bufs)
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        self._check(lib().modes_pool_ingest(self._h, _ptr(ids), ptrs, ids.size, self._fn, None))
+
+    def ingest_ptrs(self, receivers: np.ndarray, ptrs, sink=None) -> None:
+        """The same from raw host addresses (pinned memory); sink: a POOL_SINK_FN or None to drop the messages."""
+        fn = sink if sink is not None else C.cast(None, POOL_SINK_FN)
+        self._check(lib().modes_pool_ingest(self._h, _ptr(receivers), ptrs, receivers.size, fn, None))
+
+    def resolve(self, receivers, cands: np.ndarray, tiles: np.ndarray) -> None:
+        """The host half alone over records of a batch laid out pad, data, pad, data, ..."""
+        ids = np.ascontiguousarray(receivers, dtype=np.uint32)
+        cands = np.ascontiguousarray(cands); tiles = np.ascontiguousarray(tiles)
+        assert tiles.size == tiles_for(2 * ids.size)
+        self._check(lib().modes_pool_resolve(self._h, _ptr(ids), ids.size, _ptr(cands), _ptr(tiles), self._fn, None))
+
+    def take(self, receiver: int) -> list:
+        out, self.messages[receiver] = self.messages[receiver], []
+        return out
+
+    def set_output_array(self, capacity: int):
+        """Messages of all receivers into one array (+ the receiver of each), restarted by rearm_output()."""
+        self._out = (Message * capacity)()
+        self._out_rx = np.zeros(capacity, dtype=np.uint32)
+        self._check(lib().modes_pool_set_output(self._h, C.addressof(self._out), _ptr(self._out_rx), capacity))
+        return self._out, self._out_rx
+
+    def rearm_output(self) -> None:
+        self._check(lib().modes_pool_set_output(self._h, C.addressof(self._out), _ptr(self._out_rx), len(self._out)))
+
+    def output_count(self) -> int:
+        return int(lib().modes_pool_output_count(self._h))
+
+    def stats(self, receiver: int) -> dict:
+        st = Stats()
+        lib().modes_pool_stats(self._h, receiver, C.byref(st))
+        return dict(zip(STAT_NAMES, [int(x) for x in st.v]))
+
+    def buffers(self, receiver: int) -> int:
+        return int(lib().modes_pool_buffers(self._h, receiver))
+
+    def reset(self, receiver: int) -> None:
+        lib().modes_pool_reset(self._h, receiver)
+        self.messages[receiver] = []
+
+    def close(self):
+        if self._h:
+            lib().modes_pool_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
 
     def __del__(self):
         try:

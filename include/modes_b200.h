@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define MODES_B200_ABI_VERSION 2
+#define MODES_B200_ABI_VERSION 3
 
 /* Sizes fixed by the reference's buffering (dump1090.c:54, :61, :331). */
 #define MODES_BUFFER_BYTES    262144      /* MODES_DATA_LEN: new bytes per reference buffer */
@@ -342,6 +342,41 @@ uint64_t modes_launch_count(const modes_ctx *ctx);
 int  modes_set_host_wait(int mode);
 /* Entries of the tile table of a batch of n_buffers reference buffers. */
 size_t modes_tile_count(size_t n_buffers);
+
+/* ---- many receivers on one GPU (batch across receivers, not across time) ----
+ * One dump1090 process serves one RTL-SDR: rtlsdrCallback (dump1090.c:442-456) fills one buffer of
+ * 131072 samples at a time, readDataFromFile/rtlsdrCallback prefix it with the last 238 samples of the
+ * previous one (:481-485), and detectModeS keeps ONE address cache, skip state and set of statistics.
+ * A pool keeps all of that per receiver for many independent 2 MHz streams and decodes one buffer of each
+ * of them in ONE batch on the device (csrc/modes_pool.cpp: each buffer rides behind a resident pad buffer
+ * whose tail is that receiver's carry, so the kernels are the single-stream ones).  Messages of a
+ * receiver are delivered in its stream order with sample_pos counted in its own stream; receivers are
+ * served in the order they are listed.  Every receiver's output equals a modes_ctx fed that receiver's
+ * buffers alone. */
+typedef struct modes_pool modes_pool;
+typedef void (*modes_pool_sink_fn)(void *user, uint32_t receiver, const modes_message *mm);
+/* max_batch_receivers: most receivers one modes_pool_ingest call names (0: n_receivers); sizes the
+ * resident batch (2 x 256 KiB per receiver).  No device is touched before the first modes_pool_ingest. */
+modes_pool *modes_pool_create(const modes_config *cfg, size_t n_receivers, size_t max_batch_receivers);
+void        modes_pool_destroy(modes_pool *p);
+const char *modes_pool_last_error(const modes_pool *p);
+/* iq[i]: the next MODES_BUFFER_BYTES of receiver receivers[i] (host memory, pinned for full speed); a
+ * receiver may be named once per call and need not be named in every call. */
+int  modes_pool_ingest(modes_pool *p, const uint32_t *receivers, const uint8_t *const *iq, size_t n,
+                       modes_pool_sink_fn sink, void *user);
+/* The host half alone, for candidate records produced elsewhere over a batch laid out as the pool lays
+ * it out: buffer 2i = pad buffer of receivers[i] (no signal, last MODES_CARRY_BYTES = its carry), buffer
+ * 2i+1 = its new buffer; candidates/tiles as modes_detect_fetch returns them for those 2n buffers. */
+int  modes_pool_resolve(modes_pool *p, const uint32_t *receivers, size_t n, const modes_candidate *candidates,
+                        const modes_tile *tiles, modes_pool_sink_fn sink, void *user);
+/* Like modes_set_output: messages are ALSO written to a caller-owned array, all receivers' in delivery
+ * order, receiver_of[k] naming the receiver of out[k]; the count keeps running past capacity, calling
+ * it again restarts the array.  NULL, NULL, 0 turns it off.  The sink may then be NULL. */
+int    modes_pool_set_output(modes_pool *p, modes_message *out, uint32_t *receiver_of, size_t capacity);
+size_t modes_pool_output_count(const modes_pool *p);
+int  modes_pool_stats(const modes_pool *p, uint32_t receiver, modes_stats *out);
+int  modes_pool_reset(modes_pool *p, uint32_t receiver);        /* the receiver starts a new stream */
+int64_t modes_pool_buffers(const modes_pool *p, uint32_t receiver);   /* buffers of it decoded so far */
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(str(api.LIB_PATH))
     for name in sorted(declared):
         assert hasattr(L, name), name
-    assert L.modes_abi_version() == 2
+    assert L.modes_abi_version() == 3
 
 
 def test_struct_layouts():
