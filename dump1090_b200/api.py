@@ -118,7 +118,8 @@ EXPORTS = ["modes_abi_version", "modes_default_config", "modes_create", "modes_d
            "modes_tracker_list", "modes_tracker_expire", "modes_tracker_reference", "modes_tracker_format_json",
            "modes_tracker_format_table", "modes_format_sbs", "modes_cpr_nl",
            "modes_pool_create", "modes_pool_destroy", "modes_pool_last_error", "modes_pool_ingest", "modes_pool_resolve",
-           "modes_pool_stats", "modes_pool_reset", "modes_pool_buffers", "modes_pool_set_output", "modes_pool_output_count"]
+           "modes_pool_stats", "modes_pool_reset", "modes_pool_buffers", "modes_pool_set_output", "modes_pool_output_count",
+           "modes_pool_submit", "modes_pool_collect"]
 
 
 def lib():
@@ -199,6 +200,8 @@ def lib():
         L.modes_pool_last_error.restype = C.c_char_p
         L.modes_pool_last_error.argtypes = [C.c_void_p]
         L.modes_pool_ingest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, POOL_SINK_FN, C.c_void_p]
+        L.modes_pool_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.modes_pool_collect.argtypes = [C.c_void_p, POOL_SINK_FN, C.c_void_p]
         L.modes_pool_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, POOL_SINK_FN, C.c_void_p]
         L.modes_pool_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(Stats)]
         L.modes_pool_reset.argtypes = [C.c_void_p, C.c_uint32]
@@ -575,6 +578,25 @@ class ReceiverPool:
         """The same from raw host addresses (pinned memory); sink: a POOL_SINK_FN or None to drop the messages."""
         fn = sink if sink is not None else C.cast(None, POOL_SINK_FN)
         self._check(lib().modes_pool_ingest(self._h, _ptr(receivers), ptrs, receivers.size, fn, None))
+
+    def submit(self, receivers, buffers) -> None:
+        """Upload + kernels, no waiting; `buffers` are kept alive until the matching collect()."""
+        ids = np.ascontiguousarray(receivers, dtype=np.uint32)
+        bufs = [np.ascontiguousarray(b, dtype=np.uint8) for b in buffers]
+        assert ids.size == len(bufs) and all(b.size == BUFFER_BYTES for b in bufs)
+        ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+        self._check(lib().modes_pool_submit(self._h, _ptr(ids), ptrs, ids.size))
+        self._inflight = getattr(self, "_inflight", []) + [(ids, bufs)]
+
+    def submit_ptrs(self, receivers: np.ndarray, ptrs) -> None:
+        self._check(lib().modes_pool_submit(self._h, _ptr(receivers), ptrs, receivers.size))
+
+    def collect(self, sink="collect") -> None:
+        """Wait for the oldest submitted batch, resolve it, deliver its messages (sink=None: only to the output array)."""
+        fn = self._fn if sink == "collect" else (sink if sink is not None else C.cast(None, POOL_SINK_FN))
+        self._check(lib().modes_pool_collect(self._h, fn, None))
+        if getattr(self, "_inflight", None):
+            self._inflight.pop(0)
 
     def resolve(self, receivers, cands: np.ndarray, tiles: np.ndarray) -> None:
         """The host half alone over records of a batch laid out pad, data, pad, data, ..."""

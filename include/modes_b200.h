@@ -364,6 +364,13 @@ const char *modes_pool_last_error(const modes_pool *p);
  * receiver may be named once per call and need not be named in every call. */
 int  modes_pool_ingest(modes_pool *p, const uint32_t *receivers, const uint8_t *const *iq, size_t n,
                        modes_pool_sink_fn sink, void *user);
+/* The two halves of modes_pool_ingest, for overlap: submit uploads the buffers and launches the kernels
+ * and returns without waiting (the buffers must stay valid until the batch is collected); collect waits
+ * for the OLDEST submitted batch, resolves it and delivers its messages.  Two batches may be in flight:
+ *     submit(k+1); collect(k);      -- batch k+1 crosses PCIe and is scanned while batch k is resolved
+ * A receiver may be named in both. */
+int  modes_pool_submit(modes_pool *p, const uint32_t *receivers, const uint8_t *const *iq, size_t n);
+int  modes_pool_collect(modes_pool *p, modes_pool_sink_fn sink, void *user);
 /* The host half alone, for candidate records produced elsewhere over a batch laid out as the pool lays
  * it out: buffer 2i = pad buffer of receivers[i] (no signal, last MODES_CARRY_BYTES = its carry), buffer
  * 2i+1 = its new buffer; candidates/tiles as modes_detect_fetch returns them for those 2n buffers. */

@@ -142,6 +142,20 @@ def test_pool_ingest_matches_single_stream_decodes(kw, checker_libs):
                 for r in part:
                     nxt[r] += 1
         _check(pool, streams, kw)
+        # two batches in flight, a receiver in both of them
+        for r in range(n_rx):
+            pool.reset(r)
+        k = 0
+        pool.submit([0, 1, 2], [streams[r][0:BUF] for r in (0, 1, 2)])
+        for k in range(1, n_buf):
+            pool.submit([2, 0, 1], [streams[r][k * BUF: (k + 1) * BUF] for r in (2, 0, 1)])
+            pool.collect()
+        pool.collect()
+        with pytest.raises(RuntimeError, match="no batch in flight"):
+            pool.collect()
+        for r in (0, 1, 2):
+            assert [m.raw_line() for m in pool.take(r)] == _expect(streams[r], kw)[0]
+            assert list(pool.stats(r).values()) == _expect(streams[r], kw)[2]
         # a receiver that starts a new stream
         pool.reset(2)
         for k in range(n_buf):
