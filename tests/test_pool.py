@@ -156,6 +156,14 @@ def test_pool_ingest_matches_single_stream_decodes(kw, checker_libs):
         for r in (0, 1, 2):
             assert [m.raw_line() for m in pool.take(r)] == _expect(streams[r], kw)[0]
             assert list(pool.stats(r).values()) == _expect(streams[r], kw)[2]
+        # all buffers of a call in one host block (constant distance): the strided upload
+        for r in range(n_rx):
+            pool.reset(r)
+        for k in range(n_buf):
+            block = np.stack([streams[r][k * BUF: (k + 1) * BUF] for r in range(5)])
+            pool.ingest(list(range(5)), [block[r] for r in range(5)])
+        for r in range(5):
+            assert [m.raw_line() for m in pool.take(r)] == _expect(streams[r], kw)[0]
         # a receiver that starts a new stream
         pool.reset(2)
         for k in range(n_buf):
