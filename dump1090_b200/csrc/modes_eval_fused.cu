@@ -9,8 +9,8 @@
 // Thread = candidate, warp = 32 consecutive candidates.  What the kernel adds around the walk:
 //  * The walk direction and scale factors depend on eight preamble samples only
 //    (applyPhaseCorrection, :1498-1517).  Each lane's first seven window words are copied to a small
-//    "preamble area" one chunk AHEAD (cp.async, behind the current chunk's evaluation), so that
-//    when a chunk is staged every lane already knows which way it will walk.
+//    "preamble area" before the chunk's windows are staged (cp.async, behind the walk of the chunk
+//    before it), so that when a chunk is staged every lane already knows which way it will walk.
 //  * The windows are staged in WALK ORDER: the words of a backwards-walked candidate are written
 //    reversed (the copy is a 4-byte cp.async per word anyway: windows are only 4-byte aligned).
 //    Every lane then reads ascending slots at compile-time offsets; row stride odd: lane l's slot

@@ -3,8 +3,10 @@
 // This is the body of detectModeS after the preamble test (dump1090.c:1653-1735: bit slicing, delta
 // gate, the phase-corrected retry of :1498-1558) and the order-independent half of
 // decodeModesMessage (:1099-1128: CRC syndrome, single/two-bit repair), written as straight
-// sequential code over the candidate's 241-sample window.  eval_serial_kernel (modes_kernels.cu)
-// runs it with lane = candidate, the 32 windows of a warp staged in shared memory.
+// sequential code over the candidate's 241-sample window, in two formulations: namespace `fused`
+// (at the end of the file: both attempts in ONE walk; eval_fused_kernel, modes_eval_fused.cu, the
+// default) and `evaluate` (two passes; eval_serial_kernel, modes_kernels.cu).  Both run with lane =
+// candidate, the 32 windows of a warp staged in shared memory.
 //
 // The file has no CUDA dependencies besides a few integer intrinsics, so the test suite also
 // compiles it for the host (tests/host_shim/) and checks the logic against the oracle without a
