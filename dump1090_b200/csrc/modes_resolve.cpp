@@ -306,8 +306,12 @@ static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const mod
 }
 
 // The verdict pass over one run of tiles: everything order-dependent, no message structs yet.
+// `b_lo`, `b_hi`: only the candidates of the buffers [b_lo, b_hi) of this record array are judged (buffer
+// numbers as in the records: t >> 17); the walk ends at the first candidate of buffer b_hi or later
+// (records are in stream order).  The whole array: 0, UINT32_MAX.
 static void judge_tiles(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
-                        size_t n_tiles, int64_t buffer_base, std::vector<Delivery> &deliveries) {
+                        size_t n_tiles, int64_t buffer_base, std::vector<Delivery> &deliveries,
+                        uint32_t b_lo = 0, uint32_t b_hi = UINT32_MAX) {
     // The kernels append a tile's records wherever the global cursor stands when the tile finishes:
     // records are contiguous per tile but the tiles lie scattered through the array, so walking them
     // in stream order is a chain of cache misses (the records were just written by DMA).  Request
@@ -321,7 +325,10 @@ static void judge_tiles(ResolveState &st, const ResolveConfig &cfg, const modes_
         }
         const modes_candidate *c = cands + tiles[ti].offset;
         for (uint32_t k = 0; k < tiles[ti].count; k++, c++) {
-            const int64_t buffer = buffer_base + (c->t >> 17);
+            const uint32_t rb = (uint32_t)(c->t >> 17);
+            if (rb < b_lo) continue;                       // the part before this one takes it
+            if (rb >= b_hi) return;                        // the next part's
+            const int64_t buffer = buffer_base + rb;
             const uint32_t j = (uint32_t)(c->t & (kBufSamples - 1));
             if (buffer != st.cur_buffer) { st.cur_buffer = buffer; st.next_j = 0; }
             if (j < st.next_j) continue;                   // inside a message already taken
@@ -395,121 +402,226 @@ void deliver_gpu(const modes_delivery *d, size_t n, int64_t buffer_base, Message
     out.count += n;
 }
 
-struct ShardRun { ResolveState start, end; std::vector<Delivery> deliveries; };
-struct ResolveScratch { std::vector<Delivery> deliveries; std::vector<ShardRun> runs; };
+// ---- parts of a stream judged concurrently, exactly
+//
+// The only state that crosses a buffer boundary is the ICAO address cache (the skip state restarts
+// at every reference buffer, dump1090.c:1593).  A stream is therefore cut into PARTS of whole
+// buffers — the shards of a multi-GPU decode, and each long shard once more into a few parts for
+// this host's threads — and part k is judged from a GUESS of the cache at its start: first the
+// cache the call started with, overwritten by what the tail of part k-1 writes; in later rounds the
+// cache part k-1 ended with in the previous round.  The guess is verified afterwards against the
+// cache part k-1 really ended with, and a part whose guess was wrong is simply judged again.  One
+// round normally suffices; in the worst case the loop degenerates to the sequential order, never
+// to a wrong result.
+struct Part {
+    const modes_candidate *cands; const modes_tile *tiles; size_t n_tiles;   // the record array the part lies in
+    size_t tile_lo;              // first tile that can hold one of its candidates
+    uint32_t b_lo, b_hi;         // its buffers, as numbered in the records (t >> 17)
+    int64_t buffer_base;
+    bool first_of_shard;         // the tail pass for a shard's first part walks the previous SHARD's array
+};
+struct PartRun { ResolveState start, end; std::vector<Delivery> deliveries; };
+struct ResolveScratch {
+    std::vector<Delivery> deliveries;
+    std::vector<PartRun> runs;   // kept between calls: delivery lists keep their capacity (growing them from nothing
+                                 // in every call costs more in page faults, taken concurrently, than the verdicts)
+    size_t n_runs_held = 0;      // > 0: a tentative resolve left its deliveries in runs[0 .. n_runs_held)
+};
 ResolveScratch *scratch_create() { return new (std::nothrow) ResolveScratch(); }
 void scratch_destroy(ResolveScratch *s) { delete s; }
+
+// How many parts a record array of n_tiles tiles is worth on this host: a part should be long
+// enough (default 4096 tiles = 32 M samples) to repay its thread and its tail pass, and there is no
+// point in more parts than threads.  MODES_RESOLVE_PARTS = 1 keeps the sequential pass;
+// MODES_RESOLVE_PART_TILES sets the minimum part length (tests use small values).
+static size_t parts_for(size_t n_tiles) {
+    static const unsigned budget = host_cpu_budget();
+    auto env_num = [](const char *name) { const char *e = std::getenv(name); return e ? std::atol(e) : 0L; };
+    const long env_parts = env_num("MODES_RESOLVE_PARTS"), env_tiles = env_num("MODES_RESOLVE_PART_TILES");
+    size_t max_parts = budget >= 16 ? 8 : (budget >= 4 ? budget / 2 : 1);
+    const long share = env_num("MODES_BUILD_THREADS");                   // the caller's share of a host it shares with other ranks
+    if (share >= 1 && (size_t)share < max_parts) max_parts = (size_t)share;
+    if (env_parts > 0) max_parts = (size_t)env_parts;
+    const size_t min_tiles = env_tiles > 0 ? (size_t)env_tiles : 4096;
+    size_t p = n_tiles / min_tiles;
+    if (p > max_parts) p = max_parts;
+    return p < 1 ? 1 : p;
+}
+
+// Cut one record array into up to `want` parts at buffer boundaries.  The boundary of part k is
+// read from the records themselves: the buffer after the one the first candidate at or behind tile
+// k * n_tiles / want lies in (tiles do not line up with buffers; records are in stream order).
+static void cut_parts(const modes_candidate *cands, const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, size_t want,
+                      std::vector<Part> &parts) {
+    Part p{cands, tiles, n_tiles, 0, 0, UINT32_MAX, buffer_base, true};
+    for (size_t k = 1; k < want; k++) {
+        size_t ti = k * n_tiles / want;
+        while (ti < n_tiles && tiles[ti].count == 0) ti++;
+        if (ti >= n_tiles) break;
+        const uint32_t b = (uint32_t)(cands[tiles[ti].offset].t >> 17) + 1;      // first buffer of the next part
+        if (b <= p.b_lo) continue;                                                 // (a gap longer than a part)
+        p.b_hi = b;
+        parts.push_back(p);
+        p.tile_lo = ti; p.b_lo = b; p.b_hi = UINT32_MAX; p.first_of_shard = false;
+    }
+    parts.push_back(p);
+}
+
+// Judge the parts (rounds of guess and verify, see above); runs[k] receives part k's deliveries
+// and statistics, `st` the state after the last part.
+static int judge_parts(ResolveState &st, const ResolveConfig &cfg, const std::vector<Part> &parts, PartRun *runs) {
+    const size_t n = parts.size();
+    ResolveState blank;
+    blank.reset();
+    auto run_part = [&](size_t k, const ResolveState &from) {
+        PartRun &r = runs[k];
+        const Part &p = parts[k];
+        r.start = from;
+        std::memset(r.start.stats, 0, sizeof(r.start.stats));
+        if (k) { r.start.cur_buffer = -1; r.start.next_j = 0; }           // a part starts a buffer
+        r.end = r.start;
+        r.deliveries.clear();
+        judge_tiles(r.end, cfg, p.cands, p.tiles + p.tile_lo, p.n_tiles - p.tile_lo, p.buffer_base, r.deliveries, p.b_lo, p.b_hi);
+    };
+    int rounds = 0;
+    size_t done = 0;                                       // parts [0, done) are final
+    for (int round = 0; done < n; round++, rounds++) {
+        // fix every guess before any thread of this round starts rewriting runs[*].end
+        std::vector<ResolveState> guess(n);
+        std::vector<char> rerun(n, 0);
+        for (size_t k = done; k < n; k++) {
+            guess[k] = (k == done) ? (done ? runs[done - 1].end : st) : (round ? runs[k - 1].end : blank);
+            rerun[k] = round == 0 || k == done || std::memcmp(guess[k].icao, runs[k].start.icao, sizeof(blank.icao)) != 0;
+        }
+        auto job = [&](size_t k) {
+            if (!(round == 0 && k > done)) { run_part(k, guess[k]); return; }
+            // First guess: the cache this call started with, overwritten by what the LAST SIXTEENTH of
+            // part k-1 writes (addresses are re-confirmed every second or so, so the tail of a long
+            // part has normally written every slot the whole part leaves changed).
+            const Part &q = parts[k - 1];
+            ResolveState g = st;
+            g.cur_buffer = -1; g.next_j = 0;
+            const size_t end_tile = parts[k].first_of_shard ? q.n_tiles : (parts[k].tile_lo + 1 < q.n_tiles ? parts[k].tile_lo + 1 : q.n_tiles);
+            const size_t len = end_tile - q.tile_lo;
+            size_t tail = len / 16 > 128 ? len / 16 : 128;             // at least ~1 M samples (half a second of stream)
+            if (tail > len) tail = len;
+            runs[k].deliveries.clear();
+            judge_tiles(g, cfg, q.cands, q.tiles + (end_tile - tail), q.n_tiles - (end_tile - tail), q.buffer_base, runs[k].deliveries,
+                        q.b_lo, q.b_hi);
+            run_part(k, g);
+        };
+        std::vector<std::thread> th;
+        size_t mine = n;                                   // the caller judges one part itself
+        for (size_t k = done; k < n; k++) {
+            if (!rerun[k]) continue;
+            if (mine == n) { mine = k; continue; }
+            th.emplace_back(job, k);
+        }
+        if (mine < n) job(mine);
+        for (auto &t : th) t.join();
+        // accept the longest verified prefix
+        for (; done < n; done++) {
+            const ResolveState &truth = done ? runs[done - 1].end : st;
+            if (std::memcmp(truth.icao, runs[done].start.icao, sizeof(truth.icao)) != 0) break;
+        }
+    }
+    for (size_t k = 0; k < n; k++)
+        for (int i = 0; i < 8; i++) st.stats[i] += runs[k].end.stats[i];
+    if (n) {
+        std::memcpy(st.icao, runs[n - 1].end.icao, sizeof(st.icao));
+        // the skip state is that of the last part that saw a candidate (an empty part leaves none)
+        for (size_t k = n; k-- > 0;)
+            if (runs[k].end.cur_buffer != -1 || k == 0) { st.cur_buffer = runs[k].end.cur_buffer; st.next_j = runs[k].end.next_j; break; }
+    }
+    return rounds;
+}
+
+static PartRun *runs_for(ResolveScratch *scratch, size_t n) {
+    if (scratch->runs.size() < n) scratch->runs.resize(n);
+    return scratch->runs.data();
+}
 
 void resolve_candidates(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands,
                         const modes_tile *tiles, size_t n_tiles, int64_t buffer_base, MessageOut &out,
                         ResolveScratch *scratch) {
-    std::vector<Delivery> &deliveries = scratch->deliveries;
-    deliveries.clear();
-    static const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
-    const auto t0 = std::chrono::steady_clock::now();
-    judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, deliveries);
-    const auto t1 = std::chrono::steady_clock::now();
-    deliver(deliveries, out);
+    const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
+    scratch->n_runs_held = 0;
+    const size_t want = parts_for(n_tiles);
+    if (want <= 1) {
+        std::vector<Delivery> &deliveries = scratch->deliveries;
+        deliveries.clear();
+        judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, deliveries);
+        const auto t1 = now();
+        deliver(deliveries, out);
+        if (timing) std::fprintf(stderr, "resolve_candidates: %zu tiles, verdicts %.2f ms, structs %.2f ms\n", n_tiles, ms(t0, t1), ms(t1, now()));
+        return;
+    }
+    std::vector<Part> parts;
+    cut_parts(cands, tiles, n_tiles, buffer_base, want, parts);
+    PartRun *runs = runs_for(scratch, parts.size());
+    const int rounds = judge_parts(st, cfg, parts, runs);
+    const auto t1 = now();
+    for (size_t k = 0; k < parts.size(); k++) deliver(runs[k].deliveries, out);
     if (timing)
-        std::fprintf(stderr, "resolve_candidates: %zu tiles, verdicts %.2f ms, structs %.2f ms\n", n_tiles,
-                     std::chrono::duration<double, std::milli>(t1 - t0).count(),
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+        std::fprintf(stderr, "resolve_candidates: %zu tiles in %zu parts, %d rounds, verdicts %.2f ms, structs %.2f ms\n", n_tiles,
+                     parts.size(), rounds, ms(t0, t1), ms(t1, now()));
 }
 
 void resolve_tentative(ResolveState &st, const ResolveConfig &cfg, const modes_candidate *cands, const modes_tile *tiles,
                        size_t n_tiles, int64_t buffer_base, ResolveScratch *scratch) {
     scratch->deliveries.clear();
-    judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, scratch->deliveries);
+    scratch->n_runs_held = 0;
+    const size_t want = parts_for(n_tiles);
+    if (want <= 1) {
+        judge_tiles(st, cfg, cands, tiles, n_tiles, buffer_base, scratch->deliveries);
+        return;
+    }
+    std::vector<Part> parts;
+    cut_parts(cands, tiles, n_tiles, buffer_base, want, parts);
+    judge_parts(st, cfg, parts, runs_for(scratch, parts.size()));
+    scratch->n_runs_held = parts.size();
 }
 
 void resolve_commit(MessageOut &out, ResolveScratch *scratch) {
+    if (scratch->n_runs_held) {
+        for (size_t k = 0; k < scratch->n_runs_held; k++) { deliver(scratch->runs[k].deliveries, out); scratch->runs[k].deliveries.clear(); }
+        scratch->n_runs_held = 0;
+        return;
+    }
     deliver(scratch->deliveries, out);
     scratch->deliveries.clear();
 }
 
-// Several shards of one stream (e.g. one per GPU), resolved concurrently and exactly.
-//
-// The only state that crosses a shard boundary is the ICAO address cache (skip state restarts at
-// every reference buffer, and shards are whole buffers).  Shard k is therefore resolved from a
-// GUESS of the cache at its start — first the call's starting cache overwritten by the tail of
-// shard k-1, in later rounds the cache shard k-1 ended with in the previous round — and the guess
-// is verified afterwards against the cache shard k-1 really ended with.  A shard whose guess was
-// wrong is simply resolved again.  One round normally suffices; in the worst case the loop
-// degenerates to the sequential order, never to a wrong result.
+// Several shards of one stream (e.g. one per GPU), resolved concurrently and exactly: every shard
+// is a part, long shards are cut once more (see judge_parts).
 void resolve_shards(ResolveState &st, const ResolveConfig &cfg, size_t n_shards, const modes_candidate *const *cands,
                     const modes_tile *const *tiles, const size_t *n_tiles, const int64_t *buffer_base,
                     MessageOut &out, ResolveScratch *scratch) {
-    // Delivery lists keep their capacity from call to call (growing them from nothing in every
-    // call costs more in page faults, taken concurrently by the shard threads, than the verdicts).
-    using Run = ShardRun;
-    if (scratch->runs.size() < n_shards) scratch->runs.resize(n_shards);
-    Run *const runs = scratch->runs.data();
-    ResolveState blank;
-    blank.reset();
-    auto run_shard = [&](size_t k, const ResolveState &from) {
-        Run &r = runs[k];
-        r.start = from;
-        std::memset(r.start.stats, 0, sizeof(r.start.stats));
-        r.end = r.start;
-        r.deliveries.clear();
-        judge_tiles(r.end, cfg, cands[k], tiles[k], n_tiles[k], buffer_base[k], r.deliveries);
-    };
     const bool timing = std::getenv("MODES_RESOLVE_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto t_start = now();
-    int rounds = 0;
-    size_t done = 0;                                       // shards [0, done) are final
-    for (int round = 0; done < n_shards; round++, rounds++) {
-        // fix every guess before any thread of this round starts rewriting runs[*].end
-        std::vector<ResolveState> guess(n_shards);
-        std::vector<char> rerun(n_shards, 0);
-        for (size_t k = done; k < n_shards; k++) {
-            guess[k] = (k == done) ? (done ? runs[done - 1].end : st) : (round ? runs[k - 1].end : blank);
-            rerun[k] = round == 0 || k == done || std::memcmp(guess[k].icao, runs[k].start.icao, sizeof(blank.icao)) != 0;
-        }
-        std::vector<std::thread> th;
-        for (size_t k = done; k < n_shards; k++) {
-            if (!rerun[k]) continue;
-            if (round == 0 && k > done) {
-                // First guess: the cache this call started with, overwritten by what the LAST SIXTEENTH of
-                // shard k-1 writes (addresses are re-confirmed every second or so, so the tail of a long
-                // shard has normally written every slot the whole shard leaves changed).
-                th.emplace_back([&, k] {
-                    ResolveState g = st;
-                    g.cur_buffer = -1; g.next_j = 0;
-                    const size_t nt = n_tiles[k - 1];
-                    size_t tail = nt / 16 > 128 ? nt / 16 : 128;       // at least ~1 M samples (half a second of stream)
-                    if (tail > nt) tail = nt;
-                    runs[k].deliveries.clear();
-                    judge_tiles(g, cfg, cands[k - 1], tiles[k - 1] + (nt - tail), tail, buffer_base[k - 1], runs[k].deliveries);
-                    g.cur_buffer = -1; g.next_j = 0;
-                    run_shard(k, g);
-                });
-            } else {
-                th.emplace_back([&, k] { run_shard(k, guess[k]); });
-            }
-        }
-        for (auto &t : th) t.join();
-        // accept the longest verified prefix
-        for (; done < n_shards; done++) {
-            const ResolveState &truth = done ? runs[done - 1].end : st;
-            if (std::memcmp(truth.icao, runs[done].start.icao, sizeof(truth.icao)) != 0) break;
-        }
-    }
-    auto t_judged = now();
+    scratch->n_runs_held = 0;
+    std::vector<Part> parts;
+    size_t threads_left = parts_for((size_t)-1);
     for (size_t k = 0; k < n_shards; k++) {
-        for (int i = 0; i < 8; i++) st.stats[i] += runs[k].end.stats[i];
-        deliver(runs[k].deliveries, out);
+        size_t want = parts_for(n_tiles[k]);
+        const size_t share = threads_left / (n_shards - k) > 0 ? threads_left / (n_shards - k) : 1;
+        if (want > share) want = share;
+        cut_parts(cands[k], tiles[k], n_tiles[k], buffer_base[k], want, parts);
+        threads_left = threads_left > want ? threads_left - want : 0;
     }
+    PartRun *runs = runs_for(scratch, parts.size());
+    const int rounds = judge_parts(st, cfg, parts, runs);
+    auto t_judged = now();
+    for (size_t k = 0; k < parts.size(); k++) deliver(runs[k].deliveries, out);
     if (timing)
-        std::fprintf(stderr, "resolve_shards: %zu shards, %d rounds, verdicts %.2f ms, structs %.2f ms\n", n_shards, rounds,
-                     std::chrono::duration<double, std::milli>(t_judged - t_start).count(),
+        std::fprintf(stderr, "resolve_shards: %zu shards in %zu parts, %d rounds, verdicts %.2f ms, structs %.2f ms\n", n_shards,
+                     parts.size(), rounds, std::chrono::duration<double, std::milli>(t_judged - t_start).count(),
                      std::chrono::duration<double, std::milli>(now() - t_judged).count());
-    if (n_shards) {
-        std::memcpy(st.icao, runs[n_shards - 1].end.icao, sizeof(st.icao));
-        st.cur_buffer = runs[n_shards - 1].end.cur_buffer;
-        st.next_j = runs[n_shards - 1].end.next_j;
-    }
 }
 
 }  // namespace modes
