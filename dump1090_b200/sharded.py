@@ -103,10 +103,13 @@ def resolve_gathered(resolver, gathered, plan) -> None:
 
 class ShmExchange:
     """all_gather of small uint32 vectors between the ranks of ONE node through a file in /dev/shm:
-    every rank owns a row [seq, payload...], writes its payload then bumps its sequence number, and
-    polls the others' — microseconds instead of the milliseconds of a gloo ring over loopback
-    (measured: the resolve worker of a 4-rank job spent a third of its time in three gloo
-    all-gathers of 8 KiB).  Create it collectively (the name travels by broadcast_object_list)."""
+    every rank owns two rows [seq, size, payload...], writes its payload into the row of the
+    exchange's parity, then its sequence number, and polls the others' — microseconds instead of the
+    milliseconds of a gloo ring over loopback (measured: the resolve worker of a 4-rank job spent a
+    third of its time in three gloo all-gathers of 8 KiB).  Two rows make one wait per exchange
+    enough: a rank overwrites the row of exchange s only in exchange s+2, which it enters after it
+    has seen every rank publish s+1, and a rank publishes s+1 only after it has read everybody's s.
+    Create it collectively (the name travels by broadcast_object_list)."""
 
     def __init__(self, dist, group=None, max_words: int = 2 * 1024):
         import os
@@ -117,12 +120,12 @@ class ShmExchange:
         name = [None]
         if self.rank == 0:
             fd, path = tempfile.mkstemp(prefix="modes_b200_xchg_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-            os.ftruncate(fd, self.world * (2 + max_words) * 4)
+            os.ftruncate(fd, self.world * 2 * (2 + max_words) * 4)
             os.close(fd)
             name[0] = path
         dist.broadcast_object_list(name, src=0, group=group)
         self.path = name[0]
-        self.mem = np.memmap(self.path, dtype=np.uint32, mode="r+", shape=(self.world, 2 + max_words))
+        self.mem = np.memmap(self.path, dtype=np.uint32, mode="r+", shape=(self.world, 2, 2 + max_words))
         self.seq = 0
         dist.barrier(group=group)
 
@@ -130,32 +133,28 @@ class ShmExchange:
         import time
         assert vec.size <= self.words
         self.seq += 1
-        row = self.mem[self.rank]
+        bank = self.seq & 1
+        row = self.mem[self.rank, bank]
         row[2: 2 + vec.size] = vec
         row[1] = vec.size
         row[0] = self.seq                                   # published last
         out = np.empty((self.world, vec.size), dtype=np.uint32)
         deadline = time.perf_counter() + 120.0
         for r in range(self.world):
-            self._await(r, deadline, "arrive")
-            out[r] = self.mem[r, 2: 2 + vec.size]
-        # nobody may overwrite its row before everybody has read it: second phase on the same counters
-        self.seq += 1
-        self.mem[self.rank, 0] = self.seq
-        for r in range(self.world):
-            self._await(r, deadline, "leave")
+            self._await(r, bank, deadline)
+            out[r] = self.mem[r, bank, 2: 2 + vec.size]
         return out
 
-    def _await(self, r: int, deadline: float, what: str):
+    def _await(self, r: int, bank: int, deadline: float):
         """Poll rank r's sequence number: yield for the first 200 us (ranks in step arrive within
         microseconds), then sleep between polls — a rank that is a whole upload late must not cost
         the waiting ranks a core each."""
         import time
         t0 = time.perf_counter()
-        while self.mem[r, 0] < self.seq:
+        while self.mem[r, bank, 0] < self.seq:
             now = time.perf_counter()
             if now > deadline:
-                raise TimeoutError(f"ShmExchange: a rank did not {what}")
+                raise TimeoutError(f"ShmExchange: rank {r} did not arrive at exchange {self.seq}")
             time.sleep(0 if now - t0 < 200e-6 else 100e-6)
 
     def close(self):

@@ -171,3 +171,39 @@ def test_bind_near_gpu_is_best_effort():
     import torch
     if not torch.cuda.is_available():
         assert info["cpus"] is None and os.sched_getaffinity(0) == before
+
+
+def _xchg_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import time
+        x = sharded.ShmExchange(dist, max_words=64)
+        rng = np.random.default_rng(100 + rank)
+        ok = True
+        for s in range(400):
+            if rng.random() < 0.2:
+                time.sleep(float(rng.random()) * 2e-3)                    # ranks drift apart by whole exchanges' worth of time
+            n = 1 + (s * 7) % 64                                          # every rank the same size in one exchange
+            got = x.all_gather(np.full(n, 1000 * s + rank, dtype=np.uint32))
+            ok &= got.shape == (world, n) and all(np.all(got[r] == 1000 * s + r) for r in range(world))
+        x.close()
+        q.put(bool(ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shm_exchange_keeps_ranks_in_step():
+    """Two rows per rank and one wait per exchange: no rank may read a row that its owner has already
+    rewritten for a later exchange, however the ranks drift."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_xchg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    assert all(q.get(timeout=10) for _ in range(world))
