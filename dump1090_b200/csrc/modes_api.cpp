@@ -362,7 +362,7 @@ int collect(modes_ctx *ctx, Slot &s) {
     if (!s.busy) return 0;
     s.busy = false;
     uint64_t n = 0;
-    static const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
+    const bool dbg = getenv("MODES_DEBUG_TIMING") != nullptr;
     const double t0 = dbg ? now_ms() : 0;
     if (wait_batch(ctx, s, &n)) return -1;
     s.busy = false;                                     // a repeated (overflowed) batch re-arms the flag
