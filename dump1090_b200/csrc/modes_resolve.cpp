@@ -358,8 +358,8 @@ static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
         const Delivery *d = deliveries.data();
         BuildPool::get().run(in_array, [=](size_t b, size_t e) {
             for (size_t i = b; i < e; i++) {
-                if (i + 6 < e) {                           // the records lie scattered (see judge_tiles): ask early
-                    const char *q = reinterpret_cast<const char *>(d[i + 6].eval);
+                if (i + 16 < e) {                           // the records lie scattered (see judge_tiles): ask early
+                    const char *q = reinterpret_cast<const char *>(d[i + 16].eval);
                     __builtin_prefetch(q, 0, 1);
                     __builtin_prefetch(q + sizeof(modes_frame_eval) - 1, 0, 1);
                 }
