@@ -122,7 +122,9 @@ def base_config(name: str, world: int) -> dict:
     """The keys both arms report identically (the driver compares the two `config` dicts)."""
     w = WORKLOADS[name]
     return {"workload": w["desc"], "flags": w["flags"], "samples_per_gpu_step": w["nbytes"] // 2,
-            "samples_per_step": world * (w["nbytes"] // 2)}
+            "samples_per_step": world * (w["nbytes"] // 2),
+            "l2_policy": "a step's input (>= 1 GiB per GPU) is larger than the 126 MB L2 (and than the host's last-level "
+                         "cache for the CPU arm); no explicit flush"}
 
 
 # ----------------------------------------------------------------------------- reference arm
@@ -641,17 +643,16 @@ def run_ours(args) -> None:
                 except Exception as e:
                     cpu_baseline["phases"] = {"error": repr(e)}
 
-        conf = base_config(name, world)
-        conf.update({"candidates_per_gpu_batch": n_cand, "device_batches_per_step": nbatch,
-                     "l2_policy": "input (>= 1 GiB per GPU) is larger than the 126 MB L2; no explicit flush",
-                     "step": "scan kernel (magnitude+preamble) + frame-evaluation kernel per device batch; every rank on its own "
-                             "shard, outputs in its own HBM, no data-path collective"})
+        conf = base_config(name, world)                      # the same dict in both arms
+        step_facts = {"candidates_per_gpu_batch": n_cand, "device_batches_per_step": nbatch,
+                      "step": "scan kernel (magnitude+preamble) + frame-evaluation kernel per device batch; every rank on its "
+                              "own shard, outputs in its own HBM, no data-path collective"}
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "Msamples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dev_ms / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic: " + what + f" to {nbytes // GIB} GiB per GPU",
-            "config": conf,
+            "config": conf, "step_facts": step_facts,
             "clocks": clocks, "gpu_launches": int(launches),
             "parity_checked": bool(parity.get("checked") and parity.get("first_64_buffers_equal_oracle")
                                    and parity.get("sequential_resolver_digest_equal") is not False),
