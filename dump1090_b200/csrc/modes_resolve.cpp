@@ -189,14 +189,15 @@ int finish_message(ResolveState &st, const modes_frame_eval &p, modes_message *o
 // What the sequential pass decides about one delivered message; the 200-byte
 // struct is built from it afterwards, in parallel for array output.
 struct Delivery {
-    const modes_frame_eval *eval;
+    modes_frame_eval eval;       // copied while the verdict pass has the record's line: the struct-building pass then
+                                 // streams through the list instead of chasing 425 744 pointers into the record array
     int64_t sample_pos;
     uint32_t iid, ap_addr;
     uint8_t crcok, phase_corrected;
 };
 
 static inline void materialise(const Delivery &d, modes_message *mm) {
-    build_message(*d.eval, d.crcok, d.iid, d.ap_addr, mm);
+    build_message(d.eval, d.crcok, d.iid, d.ap_addr, mm);
     mm->sample_pos = d.sample_pos;
     mm->phase_corrected = d.phase_corrected;
 }
@@ -301,7 +302,7 @@ static inline bool attempt(ResolveState &st, const ResolveConfig &cfg, const mod
         else { st.stats[4]++; st.stats[5]++; st.stats[6]++; }
     }
     if (cfg.check_crc == 0 || crcok)                       // dump1090.c:1803; :1772-1773
-        deliveries.push_back(Delivery{&p, sample_pos, iid, ap, (uint8_t)crcok, (uint8_t)(crcok && retry)});
+        deliveries.push_back(Delivery{p, sample_pos, iid, ap, (uint8_t)crcok, (uint8_t)(crcok && retry)});
     return crcok != 0;
 }
 
@@ -358,11 +359,6 @@ static void deliver(const std::vector<Delivery> &deliveries, MessageOut &out) {
         const Delivery *d = deliveries.data();
         BuildPool::get().run(in_array, [=](size_t b, size_t e) {
             for (size_t i = b; i < e; i++) {
-                if (i + 16 < e) {                           // the records lie scattered (see judge_tiles): ask early
-                    const char *q = reinterpret_cast<const char *>(d[i + 16].eval);
-                    __builtin_prefetch(q, 0, 1);
-                    __builtin_prefetch(q + sizeof(modes_frame_eval) - 1, 0, 1);
-                }
                 materialise(d[i], base + i);
             }
         });
