@@ -430,7 +430,7 @@ def run_ours(args) -> None:
         out_arr = resolver.set_output_array(msg_cap)
         xchg = sharded.ShmExchange(dist, host_group)     # the 4 KiB address caches travel through /dev/shm
         jobs, done = queue.Queue(), queue.Queue()
-        rounds_seen, worker_ms = [], []
+        rounds_seen, worker_ms, phase_ms = [], [], []
         pieces = nbytes // host_bytes                    # host staging is 1 GiB: larger shares go up piece by piece
         pbuf = host_bytes // api.BUFFER_BYTES
         rec_cap = (host_bytes // 2) // 64 + 4096
@@ -460,6 +460,7 @@ def run_ours(args) -> None:
                     resolver.rearm_output()
                     info = sharded.resolve_distributed(resolver, cands, tiles, rank * nbuf, dist, host_group, exchange=xchg)
                     rounds_seen.append(info["rounds"])
+                    phase_ms.append(info.get("ms") or {})
                     worker_ms.append(1e3 * (time.perf_counter() - t0))
                     done.put(None)
                 except BaseException as e:               # surface it in e2e_join()
@@ -685,6 +686,12 @@ def run_ours(args) -> None:
             out["e2e"]["host_wait"] = os.environ.get("BENCH_HOST_WAIT", "block")
             out["e2e"]["resolve_rounds_max"] = int(max(rounds_seen)) if rounds_seen else None
             out["e2e"]["resolve_worker_ms_median_rank0"] = round(float(np.median(worker_ms)), 2) if worker_ms else None
+            try:                                        # where the worker's time goes; "exchange" includes waiting for the slowest rank
+                keys = sorted({k for d in phase_ms for k in d})
+                out["e2e"]["resolve_worker_phases_ms_median_rank0"] = {
+                    k: round(float(np.median([d.get(k, 0.0) for d in phase_ms])), 2) for k in keys} if phase_ms else None
+            except Exception as e:
+                out["e2e"]["resolve_worker_phases_ms_median_rank0"] = {"error": repr(e)}
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(out), flush=True)

@@ -179,7 +179,8 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
     that rank is verified; unverified ranks run again from the now known cache.  One round is the
     rule, world rounds the worst case.  Then every rank commits (delivers) its own messages.
     `group` must accept CPU tensors (gloo); `exchange` (ShmExchange) replaces it for the 4 KiB
-    vectors on one node.  Returns {"rounds", "end_cache" (of the whole job)}."""
+    vectors on one node.  Returns {"rounds", "end_cache" (of the whole job), "ms": this rank's time in
+    the tail pass, the exchanges (waiting for the slowest rank included), the tentative runs, the commit}."""
     import torch
     world = 1 if dist is None or not dist.is_initialized() else dist.get_world_size(group)
     rank = 0 if world == 1 else dist.get_rank(group)
@@ -197,7 +198,20 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
         dist.all_gather(outs, t, group=group)
         return np.stack([o.numpy().astype(np.uint32) for o in outs])
 
-    tails = all_gather(resolver.tail_cache(cands, tiles, buffer_base)) if world > 1 else None
+    import time
+    clock = time.perf_counter
+    ms = {"tail": 0.0, "exchange": 0.0, "tentative": 0.0, "commit": 0.0}    # where this call's time went
+
+    def timed(key, fn, *a):
+        t0 = clock()
+        r = fn(*a)
+        ms[key] += 1e3 * (clock() - t0)
+        return r
+
+    tails = None
+    if world > 1:
+        mine = timed("tail", resolver.tail_cache, cands, tiles, buffer_base)
+        tails = timed("exchange", all_gather, mine)          # includes waiting for the slowest rank to get here
     guess = S0.copy()
     if rank > 0:
         t = tails[rank - 1]
@@ -206,10 +220,10 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
     while True:
         if need_run:
             resolver.set_cache(guess)
-            resolver.run_tentative(cands, tiles, buffer_base)
+            timed("tentative", resolver.run_tentative, cands, tiles, buffer_base)
             end = resolver.get_cache()
         rounds += 1
-        both = all_gather(np.concatenate([guess, end]))
+        both = timed("exchange", all_gather, np.concatenate([guess, end]))
         G, E = both[:, : api.ICAO_CACHE_SLOTS], both[:, api.ICAO_CACHE_SLOTS:]
         ok = [bool(np.array_equal(G[0], S0))]
         for k in range(1, world):
@@ -221,8 +235,8 @@ def resolve_distributed(resolver, cands: np.ndarray, tiles: np.ndarray, buffer_b
         need_run = not ok[rank]
         if need_run:
             guess = E[rank - 1].copy() if rank > 0 else S0.copy()
-    resolver.commit()
-    return {"rounds": rounds, "end_cache": E[world - 1].copy()}
+    timed("commit", resolver.commit)
+    return {"rounds": rounds, "end_cache": E[world - 1].copy(), "ms": ms}
 
 
 def gather_fixed(cands, tiles, dist, group=None, dst: int = 0, out=None):

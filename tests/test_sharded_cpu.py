@@ -114,6 +114,7 @@ def _dist_worker(rank, world, port, kind, q):
         res.set_output_array(100000)
         xchg = sharded.ShmExchange(dist) if kind.endswith("_shm") else None
         info = sharded.resolve_distributed(res, mine, _tiled(mine, count), first, dist, exchange=xchg)
+        assert set(info["ms"]) == {"tail", "exchange", "tentative", "commit"} and all(v >= 0 for v in info["ms"].values())
         if xchg:
             assert np.array_equal(xchg.all_gather(np.full(7, rank, dtype=np.uint32))[:, 0], np.arange(world))
             xchg.close()
